@@ -1,0 +1,284 @@
+/*
+ * cdr_b200.h -- C ABI of the B200 (sm_100a) implementation of the
+ * convex_dim_red alternating-update hot path.
+ *
+ * The reference (azedarach/matrix-factorization-case-studies) is pure Python:
+ * it has no FFI / plugin interface, so the drop-in boundary is its Python API
+ * (src/convex_dim_red/__init__.py:5-11).  This header is the thin C layer the
+ * Python host code (matrix-factorization-case-studies_b200/convex_dim_red)
+ * binds with ctypes; each entry point names the reference code it replaces.
+ * Citations are relative to /root/reference/src/convex_dim_red/.
+ *
+ * Conventions
+ *   - all matrix pointers are DEVICE pointers to IEEE fp64, row-major;
+ *   - every function is asynchronous on `stream` and returns 0 on success,
+ *     a positive cudaError_t if a launch failed, or a negative CDR_ERR_* code;
+ *   - nothing is allocated behind the caller's back: workspaces are passed in
+ *     and sized by the `*_workspace_bytes` twins;
+ *   - "padded" matrices have a leading dimension that is a multiple of
+ *     CDR_LD_ALIGN doubles with the padding columns zero-filled;
+ *   - `flags` (may be NULL) points at a device-resident cdr_loop_state; when
+ *     its `done` field is non-zero every kernel returns without touching
+ *     memory, so an iteration captured in a CUDA graph can be replayed past
+ *     convergence without changing the result.
+ */
+#ifndef CDR_B200_H
+#define CDR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CDR_LD_ALIGN 32          /* doubles */
+#define CDR_MAX_COMPONENTS 64    /* k <= 64 */
+#define CDR_MAX_MEMORY 8         /* non-monotone line-search memory */
+
+#define CDR_ERR_INVALID_ARGUMENT (-1)
+#define CDR_ERR_UNSUPPORTED (-2)
+#define CDR_ERR_WORKSPACE (-3)
+
+typedef void* cdr_stream_t; /* cudaStream_t */
+
+/* Options of the simplex-constrained QP solver (defaults: spg.py:287-291). */
+typedef struct cdr_spg_params {
+    double gamma;
+    double sigma_one;
+    double sigma_two;
+    double lambda_min;
+    double alpha0;
+    double alpha_min;
+    double alpha_max;
+    double epsilon_one;
+    double epsilon_two;
+    int memory;
+    int max_iterations;
+    int max_feval;
+    int use_infinity_norm;
+} cdr_spg_params;
+
+/* Device-resident control block shared by the kernels of one fit.  The
+ * `done` field must stay first (cdr_flags aliases it). */
+typedef struct cdr_loop_state {
+    int done;             /* set on convergence, failure or iteration limit */
+    int error_stage;      /* 0 none, 1 scale factors, 2 dictionary, 3 weights */
+    int n_iter;           /* completed outer iterations */
+    int converged;        /* stopping rule fired */
+    int max_iterations;
+    int stopping_rule;    /* 0 abs_delta_f, 1 rel_delta_f (archetypal_analysis.py:177-197) */
+    int require_monotone; /* archetypal_analysis.py:167-174 */
+    int spg_iter;         /* inner (dictionary) SPG iteration counter */
+    int spg_feval;
+    int spg_active;       /* inner SPG still iterating */
+    int spg_alpha_set;    /* 0 until the first step length is initialised (spg.py:178-189) */
+    int spg_warnings;     /* bit 0 step below lambda_min, bit 1 feval limit */
+    double tolerance;
+    double trace_data;    /* trace(K) or ||X||_F^2 */
+    double cost;          /* current cost */
+    double old_cost;      /* cost at the start of the outer iteration */
+    double f_old;
+    double f_new;
+    double lam;
+    double alpha;         /* spectral step length */
+    double delta;         /* <d, g> */
+    double dd;            /* <d, d> */
+    double a0;            /* linear trace term at x */
+    double a1;            /* linear trace term along d */
+    double beta;
+    double res2;
+    double resinf;
+    double penalty;       /* GPNH: lambda_W * phi(W) */
+    double f_mem[CDR_MAX_MEMORY];
+} cdr_loop_state;
+
+typedef cdr_loop_state cdr_flags;
+
+const char* cdr_version(void);
+int cdr_device_check(void); /* 0 if the current device is sm_100 */
+unsigned long long cdr_launch_count(void); /* kernels launched by this library so far */
+
+/* ------------------------------------------------------------------ simplex
+ * Euclidean projection of each row / column of A onto the probability simplex.
+ * Replaces simplex_projection.py:13-47 (simplex_project_vector / _rows /
+ * _columns).  out may alias A. */
+int cdr_simplex_project_rows(const double* A, double* out, int m, int n, long lda, long ldo,
+                             const cdr_flags* flags, cdr_stream_t stream);
+int cdr_simplex_project_columns(const double* A, double* out, int m, int n, long lda, long ldo,
+                                const cdr_flags* flags, cdr_stream_t stream);
+
+/* ------------------------------------------------------------------ per-sample QP
+ * For every sample t solve  min 1/2 z'A'z + b_t'z  over the simplex with the
+ * SPG of spg.py:286-398, where A' = diag(alpha) A diag(alpha) and
+ * b_t[c] = -alpha[c] * B[t*sb_t + c*sb_c]  (alpha may be NULL = ones).
+ * Replaces _gu_update_kernel_aa_weights / _update_kernel_aa_weights
+ * (archetypal_analysis.py:344-396) and _gu_update_gpnh_weights
+ * (gpnh_convex_coding.py:229-251).  Z (T x k, row-major) is updated in place.
+ * n_iter / n_feval (int[T], may be NULL) receive per-sample counts. */
+int cdr_quad_simplex_spg_batched(const double* A, const double* alpha, const double* B,
+                                 long sb_t, long sb_c, double* Z, int T, int k,
+                                 const cdr_spg_params* params, int* n_iter, int* n_feval,
+                                 const cdr_flags* flags, cdr_stream_t stream);
+
+/* ------------------------------------------------------------------ streaming contractions
+ * X is T x d with padded leading dimension ldx.
+ *
+ * reduce over samples:   out[k x ldo] = E (L X),  L[i][t] = Lp[i*sLi + t*sLt],
+ *   E (k x k, may be NULL = identity).  Replaces dictionary.dot(X),
+ *   X.T.dot(weights) (archetypal_analysis.py:545-549,618,641) and
+ *   weights.T.dot(X) + lstsq back-substitution (gpnh_convex_coding.py:219-224).
+ * reduce over features:  out[k x ldo] (k x T) = M X',  M is k x ldm padded.
+ *   Replaces CX.dot(X.T), X.dot(XtZ) (archetypal_analysis.py:546,549,619,642)
+ *   and X.dot(dictionary) (gpnh_convex_coding.py:271,352).
+ * gram:                  K[T x ldk] = X X' (archetypal_analysis.py:1032).
+ */
+size_t cdr_reduce_samples_workspace_bytes(int T, int d, int k);
+int cdr_reduce_samples(const double* Lp, long sLi, long sLt, const double* X, long ldx, int T,
+                       int d, int k, const double* E, double* out, long ldo, void* workspace,
+                       size_t workspace_bytes, const cdr_flags* flags, cdr_stream_t stream);
+size_t cdr_reduce_features_workspace_bytes(int T, int d, int k);
+int cdr_reduce_features(const double* M, long ldm, const double* X, long ldx, int T, int d,
+                        int k, double* out, long ldo, void* workspace, size_t workspace_bytes,
+                        const cdr_flags* flags, cdr_stream_t stream);
+size_t cdr_gram_workspace_bytes(int T, int d);
+int cdr_gram(const double* X, long ldx, int T, int d, double* K, long ldk, void* workspace,
+             size_t workspace_bytes, cdr_stream_t stream);
+/* sum of squares of a T x d matrix (trace of the Gram, archetypal_analysis.py:552) */
+int cdr_frobenius_sq(const double* X, long ldx, int T, int d, double* out, void* workspace,
+                     size_t workspace_bytes, cdr_stream_t stream);
+size_t cdr_frobenius_workspace_bytes(void);
+/* fixed-order sum of n doubles (k-means inertia) */
+int cdr_sum_vector(const double* v, int n, double* out, cdr_stream_t stream);
+/* ||X - Z A||_F^2 with direct differences (gpnh_convex_coding.py:199-210,
+ * archetypal_analysis.py:1196-1197); Z is T x k, A is k x lda; part: T doubles */
+int cdr_residual_sq(const double* X, long ldx, int T, int d, const double* Z, int k,
+                    const double* A, long lda, double* out, double* part, cdr_stream_t stream);
+
+/* ------------------------------------------------------------------ small products
+ * out[i][j] = scale * sum_n A[i*sAi + n*sAn] * B[j*sBj + n*sBn]   (mode 0)
+ * out[i][j] = scale * sum_n (A[i,n] - B[j,n])^2                    (mode 1)
+ * Up to CDR_GRAM_BATCH independent products per launch. */
+#define CDR_GRAM_BATCH 4
+typedef struct cdr_small_gram_desc {
+    const double* A;
+    const double* B;
+    double* out;      /* ka x kb, row-major, leading dimension kb */
+    long sAi, sAn, sBj, sBn;
+    int ka, kb, n, mode;
+    double scale;
+} cdr_small_gram_desc;
+size_t cdr_small_gram_workspace_bytes(void);
+int cdr_small_gram(const cdr_small_gram_desc* descs, int count, void* workspace,
+                   size_t workspace_bytes, const cdr_flags* flags, cdr_stream_t stream);
+
+/* P = pinv(S / n_samples + lambda * G) / n_samples for the symmetric k x k
+ * matrix S, G = 4/(d k (k-1)) (k I - 1); minimum-norm with the
+ * numpy.linalg.lstsq(rcond=None) cut-off.  Replaces the k x k solve of
+ * gpnh_convex_coding.py:221-226.  workspace: cdr_sym_pinv_workspace_bytes(k). */
+size_t cdr_sym_pinv_workspace_bytes(int k);
+int cdr_gpnh_solve_matrix(const double* ZtZ, int k, int n_samples, int n_features,
+                          double lambda_W, double* P, void* workspace, size_t workspace_bytes,
+                          const cdr_flags* flags, cdr_stream_t stream);
+
+/* ------------------------------------------------------------------ AA dictionary SPG steps
+ * Device-side pieces of spg() (spg.py:46-283) specialised to the AA dictionary
+ * problem (archetypal_analysis.py:261-341); see DESIGN.md for the sequence.
+ * Shapes: C, G, D, CK, DK, KZt are k x T with leading dimension ldt. */
+typedef struct cdr_aa_buffers {
+    double* C;          /* k x T dictionary (iterate x) */
+    double* G;          /* gradient */
+    double* D;          /* search direction */
+    double* CK;         /* C K  (or (C X) X') */
+    double* DK;         /* D K */
+    double* KZt;        /* (K Z)' */
+    double* alpha;      /* k scale factors */
+    double* ZtZ;        /* k x k */
+    double* CKCt;       /* k x k */
+    double* CKZ;        /* k x k */
+    double* G01;        /* k x k: CK D' */
+    double* G11;        /* k x k: DK D' */
+    double* row_scratch;/* 8 * k doubles of per-row partial results */
+    cdr_loop_state* state;
+    double* cost_deltas;/* max_iterations doubles */
+    int k, T;
+    long ldt;
+    double grad_scale;  /* 1/T (archetypal_analysis.py:297) or 1/k (:288) */
+    double cost_scale;  /* 1/k (archetypal_analysis.py:265,277) */
+} cdr_aa_buffers;
+
+/* P = pinv(S) for a symmetric k x k matrix (same cut-off) */
+int cdr_sym_pinv(const double* S, int k, double* P, const cdr_flags* flags, cdr_stream_t stream);
+/* start of an outer iteration: old_cost = cost, iteration-limit test */
+int cdr_loop_begin(cdr_loop_state* state, cdr_stream_t stream);
+/* spg.py:146-189: x = P(C) in place, f(x), df(x) -> G, first step length.
+ * CK / CKCt must correspond to the projected C. */
+int cdr_aa_spg_begin(const cdr_aa_buffers* b, const cdr_spg_params* p, cdr_stream_t stream);
+/* spg.py:191-194: D = P(x - alpha G) - x and the row partials of <D,G>, <D,D> */
+int cdr_aa_spg_direction(const cdr_aa_buffers* b, const cdr_spg_params* p, cdr_stream_t stream);
+/* spg.py:196-229: needs DK = D K and G01 = CK D', G11 = DK D'; runs the whole
+ * non-monotone Armijo search on the device and applies x += lam D, CK += lam DK */
+int cdr_aa_spg_linesearch(const cdr_aa_buffers* b, const cdr_spg_params* p, cdr_stream_t stream);
+/* spg.py:231-281: new gradient, Barzilai-Borwein step, residual test, counters */
+int cdr_aa_spg_update(const cdr_aa_buffers* b, const cdr_spg_params* p, int compute_residual,
+                      cdr_stream_t stream);
+/* cost after a sub-step and the monotonicity / convergence tests of
+ * archetypal_analysis.py:167-197, 623-663.  stage: 2 dictionary, 3 weights;
+ * end_of_iteration != 0 also applies the stopping rule and advances n_iter. */
+int cdr_aa_cost_check(const cdr_aa_buffers* b, int stage, int end_of_iteration,
+                      cdr_stream_t stream);
+/* stand-alone df(C) -> b->G and f(C) -> *out (archetypal_analysis.py:261-301) */
+int cdr_aa_gradient(const cdr_aa_buffers* b, cdr_stream_t stream);
+int cdr_aa_dictionary_cost(const cdr_aa_buffers* b, double trace_data, double* out,
+                           cdr_stream_t stream);
+
+/* ------------------------------------------------------------------ GPNH cost bookkeeping
+ * gpnh_convex_coding.py:352-399.  tr(W'X'Z) = trace of XWtZ (k x k),
+ * tr(Z'Z W'W) from the two k x k matrices; reg_pairs (k x k, may be NULL)
+ * holds ||w_i - w_j||^2. */
+int cdr_gpnh_cost_check(cdr_loop_state* state, double* cost_deltas, const double* XWtZ,
+                        const double* ZtZ, const double* WtW, const double* reg_pairs, int k,
+                        int n_samples, int n_features, double lambda_W, int stage,
+                        int end_of_iteration, cdr_stream_t stream);
+
+/* ------------------------------------------------------------------ furthest sum
+ * Greedy furthest-sum selection (furthest_sum.py:23-127) on a T x T
+ * dissimilarity matrix; also builds the dissimilarities from a Gram matrix
+ * (archetypal_analysis.py:96-100).  selected: int64[k] (device). */
+int cdr_dissimilarity_from_gram(const double* K, long ldk, int T, double* D, long ldd,
+                                cdr_stream_t stream);
+size_t cdr_furthest_sum_workspace_bytes(int T, int k, int extra_steps);
+int cdr_furthest_sum(const double* D, long ldd, int T, int k, int start_index,
+                     const int64_t* exclude, int n_exclude, int extra_steps, int64_t* selected,
+                     void* workspace, size_t workspace_bytes, cdr_stream_t stream);
+
+/* ------------------------------------------------------------------ k-means (Lloyd)
+ * Pieces of scikit-learn 1.9.0's KMeans(algorithm='lloyd') around the two
+ * streaming passes (the reference calls sklearn.cluster.KMeans at
+ * bin/run_hadisst_kmeans.py:128-131):
+ *   xct = centres X'        -> cdr_reduce_features
+ *   labels: first argmin_j ||c_j||^2 - 2 xct[j][t]   (_k_means_lloyd.pyx:193-213)
+ *   sums  = one_hot(labels) X -> cdr_reduce_samples
+ *   centres = sums / counts, squared shift            (_k_means_common.pyx:215-262)
+ * labels int32[T] is read (previous labels) and written; counts int[k] must be
+ * zeroed by the caller; changed is OR-ed with 1 if any label moved. */
+int cdr_row_sqnorms(const double* C, long ldc, int k, int d, double* out, cdr_stream_t stream);
+int cdr_kmeans_labels(const double* xct, long ldt, const double* cnorm, int T, int k,
+                      int32_t* labels, double* onehot, long ldo, int* counts, int* changed,
+                      cdr_stream_t stream);
+int cdr_kmeans_sqdist(const double* X, long ldx, int T, int d, const double* C, long ldc,
+                      const int32_t* labels, double* out, cdr_stream_t stream);
+int cdr_kmeans_update(const double* sums, long lds, const double* counts, double* centres,
+                      long ldc, int k, int d, double* shift, cdr_stream_t stream);
+/* column means / variances in NumPy's row-sequential order (sklearn _kmeans.py:285-294,
+ * 1486-1493) and in-place centring X += sign * mean */
+int cdr_column_moments(const double* X, long ldx, int T, int d, double* mean, double* var,
+                       cdr_stream_t stream);
+int cdr_center_columns(double* X, long ldx, int T, int d, const double* mean, double sign,
+                       cdr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* CDR_B200_H */

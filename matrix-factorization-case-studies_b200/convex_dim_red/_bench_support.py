@@ -1,0 +1,154 @@
+"""Timing harness used by ``bench.py`` (kept in the package so the engines'
+internals stay private to it)."""
+
+import time
+
+import numpy as np
+
+from . import _backend as be
+
+
+def _make_engine(args, X, Z0, F0, Xd=None):
+    from .archetypal_analysis import _AaEngine
+    from .gpnh_convex_coding import _GpnhEngine
+    big = 10 ** 6
+    if args.workload == 'gpnh':
+        return _GpnhEngine(X, Z0, F0, lambda_W=0.0, tolerance=0.0, max_iterations=big,
+                           require_monotonic_cost_decrease=False, X_device=Xd)
+    return _AaEngine(X, Z0, F0, np.ones(F0.shape[0]), 'feature', tolerance=0.0,
+                     max_iterations=big, require_monotonic_cost_decrease=False,
+                     dictionary_solver_kwargs=dict(max_iterations=1), data_device=Xd)
+
+
+def _time_launches(fn, reps=10):
+    torch = be.torch_mod()
+    fn()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def run_benchmark(args, X, Z0, F0, rank, world, sampler):
+    torch = be.require_cuda()
+    import torch.distributed as dist
+    lib = be.library()
+    T, d = X.shape
+    k = args.components
+    Xd = be.to_device_padded(X)
+    eng = _make_engine(args, X, Z0, F0, Xd)
+    eng.initial_cost()
+    n0 = lib.cdr_launch_count()
+    eng.iteration()                                  # eager: first warm-up step
+    launches_per_step = lib.cdr_launch_count() - n0
+    graph = None if be.graphs_disabled() else be.capture_graph(eng.iteration)
+    step = graph.replay if graph is not None else eng.iteration
+    for _ in range(max(args.warmup - 1, 0)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    with sampler:
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    st = eng.state.read()
+    if args.workload == 'aa':
+        # the first (eager) AA step also rebuilds C K for the projected start: count a
+        # steady-state step instead
+        n1 = lib.cdr_launch_count()
+        eng.iteration()
+        launches_per_step = lib.cdr_launch_count() - n1
+
+    # ---- the streaming passes on their own (roofline of the dominant kernel)
+    ws = eng.ws
+    if args.workload == 'gpnh':
+        t_samples = _time_launches(lambda: be.reduce_samples(
+            eng.Z, 1, k, eng.X, T, d, k, eng.WT, ws, E=eng.P))
+        t_features = _time_launches(lambda: be.reduce_features(eng.WT, eng.X, T, d, k, eng.XWt, ws))
+        zsave = eng.Z.clone()
+        t_qp = _time_launches(lambda: (eng.Z.copy_(zsave), be.quad_simplex_spg_batched(
+            eng.WtW, None, eng.XWt, 1, eng.ldt, eng.Z, T, k, eng.params)), reps=5)
+        passes = 2
+    else:
+        t_samples = _time_launches(lambda: be.reduce_samples(
+            eng.D, eng.ldt, 1, eng.X, T, d, k, eng.tmp_kd, ws))
+        t_features = _time_launches(lambda: be.reduce_features(eng.tmp_kd, eng.X, T, d, k, eng.DK, ws))
+        zsave = eng.Z.clone()
+        t_qp = _time_launches(lambda: (eng.Z.copy_(zsave), be.quad_simplex_spg_batched(
+            eng.CKCt, eng.alpha, eng.CK, 1, eng.ldt, eng.Z, T, k, eng.w_params)), reps=5)
+        passes = 4
+    pass_bytes = 8.0 * T * d
+    slow, name = max((t_samples, 'reduce_samples_kernel'), (t_features, 'reduce_features_kernel'))
+    roofline = {'kernel': name, 'achieved': pass_bytes / (slow * 1e-3) / 1e9,
+                'algorithmic_bytes_per_launch': pass_bytes, 'ms_per_launch': slow,
+                'traffic': None}
+    kernels = {'reduce_samples_ms': t_samples, 'reduce_features_ms': t_features,
+               'reduce_samples_gbs': pass_bytes / (t_samples * 1e-3) / 1e9,
+               'reduce_features_gbs': pass_bytes / (t_features * 1e-3) / 1e9,
+               'qp_batched_ms': t_qp, 'passes_per_step': passes,
+               'step_ms': ms / args.steps,
+               'streaming_share_of_step': passes / 2.0 * (t_samples + t_features) /
+               (ms / args.steps)}
+
+    # ---- end to end through the public NumPy API (host buffers, pinned)
+    e2e = run_e2e(args, X, Z0, F0, world)
+
+    return {'value': world * args.steps / (ms * 1e-3), 'ms_per_step': ms / args.steps,
+            'clocks': sampler.summary(), 'gpu_launches': int(launches_per_step * args.steps),
+            'roofline': roofline, 'kernels': kernels, 'e2e': e2e, 'final_cost': st.cost}
+
+
+def run_e2e(args, X, Z0, F0, world):
+    """One public-API call of `steps` outer iterations: X (pinned host memory) is uploaded
+    inside the timed region, the factors and the cost history come back as NumPy arrays."""
+    torch = be.torch_mod()
+    import torch.distributed as dist
+    from . import archetypal_analysis as aa
+    from . import gpnh_convex_coding as gp
+    Xp = torch.from_numpy(X).pin_memory()
+    Xn = Xp.numpy()
+    K = args.steps
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    if args.workload == 'gpnh':
+        out = gp._iterate_gpnh_convex_coding(
+            Xn, Z0, F0, lambda_W=0.0, tolerance=0.0, max_iterations=K,
+            require_monotonic_cost_decrease=False)
+        d2h = out[0].nbytes + out[1].nbytes + 8 * K
+    else:
+        out = aa._iterate_aa(
+            Xn, Z0, F0, np.ones(F0.shape[0]), tolerance=0.0, max_iterations=K,
+            require_monotonic_cost_decrease=False,
+            dictionary_solver_kwargs=dict(max_iterations=1))
+        d2h = out[0].nbytes + out[1].nbytes + 8 * K
+    torch.cuda.synchronize()
+    elapsed = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([elapsed], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed = float(t.item())
+    h2d = X.nbytes + Z0.nbytes + F0.nbytes
+    return {'value': world * K / elapsed, 'unit': 'iterations/s',
+            'h2d_bytes_per_step': h2d / K, 'd2h_bytes_per_step': d2h / K,
+            'call': 'one _iterate_%s call of %d outer iterations (the body of fit_transform): '
+                    'X uploaded once from pinned host memory, factors read back'
+                    % ('gpnh_convex_coding' if args.workload == 'gpnh' else 'aa', K),
+            'seconds': elapsed}

@@ -1,0 +1,486 @@
+"""GPNH-regularised convex coding (reference ``gpnh_convex_coding.py``).
+
+Same public surface as the reference -- ``GPNHConvexCoding`` plus the private
+helpers its tests import (``_gpnh_cost``, ``_iterate_gpnh_convex_coding``,
+``_update_gpnh_dictionary``, ``_update_gpnh_weights``) -- with NumPy arrays in
+and out.  The alternating loop itself runs on the GPU: the data matrix is
+uploaded once, all factors and k x k statistics stay resident, the convergence
+and monotonicity tests run on the device, and one outer iteration is replayed
+from a CUDA graph.
+"""
+
+import numbers
+import time
+import warnings
+
+import numpy as np
+from sklearn.utils import check_array, check_random_state
+
+from . import _backend as be
+from .furthest_sum import dissimilarity_from_gram_device, furthest_sum_device
+from .stochastic_matrices import right_stochastic_matrix
+from .validation_utils import check_array_shape, check_unit_axis_sums
+
+INTEGER_TYPES = (numbers.Integral, np.integer)
+
+INITIALIZATION_METHODS = (None, 'random', 'furthest_sum',)
+
+_STAGES = {1: 'scale factors', 2: 'dictionary', 3: 'weights'}
+
+
+def _check_init_weights(weights, shape, whom):
+    weights = check_array(weights)
+    check_array_shape(weights, shape, whom)
+    check_unit_axis_sums(weights, whom, axis=1)
+
+
+def _check_init_dictionary(dictionary, shape, whom):
+    dictionary = check_array(dictionary)
+    check_array_shape(dictionary, shape, whom)
+
+
+class _GpnhEngine:
+    """Device-resident state of one GPNH fit (gpnh_convex_coding.py:282-402)."""
+
+    def __init__(self, X, weights, dictionary, lambda_W=0.0, tolerance=1e-6,
+                 max_iterations=1000, stopping_criterion='abs_delta_f',
+                 require_monotonic_cost_decrease=True, weights_solver_kwargs=None,
+                 update_dictionary=True, update_weights=True, trace_XtX=None,
+                 X_device=None):
+        torch = be.require_cuda()
+        self.T, self.d = X.shape
+        self.k = weights.shape[1]
+        if self.k > be.MAX_COMPONENTS:
+            raise ValueError('n_components > %d is not supported by the B200 build'
+                             % be.MAX_COMPONENTS)
+        T, d, k = self.T, self.d, self.k
+        self.lambda_W = float(lambda_W)
+        self.update_dictionary = update_dictionary
+        self.update_weights = update_weights
+        self.params = be.make_spg_params(weights_solver_kwargs)
+        self.X = X_device if X_device is not None else be.to_device_padded(X)
+        self.ldx = self.X.stride(0)
+        self.ldt = be.round_up(T)
+        self.Z = be.to_device(weights)
+        self.WT = be.to_device_padded(np.ascontiguousarray(np.asarray(dictionary).T))
+        self.XWt = be.zeros(k, self.ldt)
+        self.ZtZ = be.zeros(k, k)
+        self.WtW = be.zeros(k, k)
+        self.XWtZ = be.zeros(k, k)
+        self.REG = be.zeros(k, k)
+        self.P = be.zeros(k, k)
+        self.ws = be.Workspace(T, d, k)
+        self.state = be.DeviceState(tolerance, max_iterations, stopping_criterion,
+                                    require_monotonic_cost_decrease)
+        if trace_XtX is None:
+            # gpnh_convex_coding.py:302 forms the d x d product only for its trace
+            trace_XtX = float(be.frobenius_sq(self.X, T, d).item())
+        self.state.write_field('trace_data', float(trace_XtX))
+        self.lib = be.library()
+        self._graph = None
+
+    # -- small products -----------------------------------------------------
+    def _desc_ZtZ(self):
+        k, T = self.k, self.T
+        return (self.Z, 1, k, k, self.Z, 1, k, k, T, self.ZtZ, 1.0, 0)
+
+    def _desc_WtW(self):
+        k, d = self.k, self.d
+        return (self.WT, self.ldx, 1, k, self.WT, self.ldx, 1, k, d, self.WtW, 1.0, 0)
+
+    def _desc_XWtZ(self):
+        k, T = self.k, self.T
+        return (self.XWt, self.ldt, 1, k, self.Z, 1, k, k, T, self.XWtZ, 1.0, 0)
+
+    def _desc_REG(self):
+        k, d = self.k, self.d
+        return (self.WT, self.ldx, 1, k, self.WT, self.ldx, 1, k, d, self.REG, 1.0, 1)
+
+    def _cost_check(self, stage, end, with_reg):
+        be.check(self.lib.cdr_gpnh_cost_check(
+            self.state.ptr, self.state.cost_deltas.data_ptr(), self.XWtZ.data_ptr(),
+            self.ZtZ.data_ptr(), self.WtW.data_ptr(),
+            self.REG.data_ptr() if with_reg else None, self.k, self.T, self.d, self.lambda_W,
+            stage, int(end), be.stream_ptr()), 'cdr_gpnh_cost_check')
+
+    # -- pieces of the loop -------------------------------------------------
+    def initial_cost(self):
+        """gpnh_convex_coding.py:292-314."""
+        flags = self.state.ptr
+        be.reduce_features(self.WT, self.X, self.T, self.d, self.k, self.XWt, self.ws, flags)
+        descs = [self._desc_ZtZ(), self._desc_WtW(), self._desc_XWtZ()]
+        if self.lambda_W != 0:
+            descs.append(self._desc_REG())
+        be.small_gram(descs, self.ws, flags)
+        self._cost_check(0, False, self.lambda_W != 0)
+
+    def dictionary_step(self, stage=2, end=False, flags=True):
+        """gpnh_convex_coding.py:348-369 (one pass Z'X with the k x k solve folded
+        into the epilogue, one pass X W)."""
+        fl = self.state.ptr if flags else None
+        T, d, k = self.T, self.d, self.k
+        be.check(self.lib.cdr_gpnh_solve_matrix(
+            self.ZtZ.data_ptr(), k, T, d, self.lambda_W, self.P.data_ptr(), None, 0, fl,
+            be.stream_ptr()), 'cdr_gpnh_solve_matrix')
+        be.reduce_samples(self.Z, 1, k, self.X, T, d, k, self.WT, self.ws, E=self.P, flags=fl)
+        be.reduce_features(self.WT, self.X, T, d, k, self.XWt, self.ws, fl)
+        descs = [self._desc_WtW(), self._desc_XWtZ()]
+        if self.lambda_W != 0:
+            descs.append(self._desc_REG())
+        be.small_gram(descs, self.ws, fl)
+        if stage is not None:
+            self._cost_check(stage, end, self.lambda_W != 0)
+
+    def weights_step(self, stage=3, end=True, flags=True):
+        """gpnh_convex_coding.py:371-384."""
+        fl = self.state.ptr if flags else None
+        be.quad_simplex_spg_batched(self.WtW, None, self.XWt, 1, self.ldt, self.Z, self.T,
+                                    self.k, self.params, flags=fl)
+        be.small_gram([self._desc_ZtZ(), self._desc_XWtZ()], self.ws, fl)
+        if stage is not None:
+            self._cost_check(stage, end, False)
+
+    def iteration(self):
+        be.check(self.lib.cdr_loop_begin(self.state.ptr, be.stream_ptr()), 'cdr_loop_begin')
+        if self.update_dictionary:
+            self.dictionary_step(end=not self.update_weights)
+        if self.update_weights:
+            self.weights_step()
+
+    # -- driver -------------------------------------------------------------
+    def run(self, verbose=0, use_graph=None):
+        torch = be.torch_mod()
+        if use_graph is None:
+            use_graph = not be.graphs_disabled()
+        self.initial_cost()
+        max_it = self.state.max_iterations
+        start = time.perf_counter()
+        launched = 0
+        st = None
+        if verbose:
+            print("*** GPNH convex coding: n_components = {:d} ***".format(self.k))
+            print('{:<12s} | {:<13s} | {:<13s}'.format('Iteration', 'Cost', 'Cost delta'))
+            print(100 * '-')
+        # first iteration eagerly (also warms up every kernel before capture)
+        self.iteration()
+        launched += 1
+        st = self.state.read()
+        chunk = 1
+        graph = None
+        while not st.done and launched < max_it:
+            if use_graph and graph is None and not verbose:
+                graph = be.capture_graph(self.iteration)
+            n = min(chunk, max_it - launched)
+            for _ in range(n):
+                if graph is not None:
+                    graph.replay()
+                else:
+                    self.iteration()
+            launched += n
+            st = self.state.read()
+            if verbose:
+                print('{:12d} | {: 12.6e} | {: 12.6e}'.format(
+                    st.n_iter, st.cost, st.cost - st.old_cost))
+            elif chunk < 32:
+                chunk *= 2
+        torch.cuda.synchronize()
+        elapsed = time.perf_counter() - start
+        st = self.state.read()
+        if st.error_stage:
+            raise RuntimeError('factorization cost increased after {} update'.format(
+                _STAGES[st.error_stage]))
+        done_iters = max(st.n_iter, 1)
+        self.cost = st.cost
+        self.n_iter = st.n_iter - 1            # the reference returns the 0-based loop index
+        self.avg_time_per_iter = elapsed / done_iters
+        self.cost_deltas = self.state.cost_deltas[:st.n_iter].cpu().numpy().tolist()
+        return self
+
+    def weights(self):
+        return be.to_host(self.Z)
+
+    def dictionary(self):
+        # d x k view of the k x d solution, like `sol.T` at gpnh_convex_coding.py:226
+        return be.to_host(self.WT, self.k, self.d).T
+
+
+def _gpnh_regularization(dictionary):
+    """Evaluate GPNH regularization term (gpnh_convex_coding.py:179-196)."""
+    dictionary = np.asarray(dictionary, dtype=np.float64)
+    n_features, n_components = dictionary.shape
+    if n_components == 1:
+        return 0.0
+    WT = be.to_device_padded(np.ascontiguousarray(dictionary.T))
+    REG = be.zeros(n_components, n_components)
+    ws = be.Workspace(1, n_features, n_components)
+    ld = WT.stride(0)
+    be.small_gram([(WT, ld, 1, n_components, WT, ld, 1, n_components, n_features, REG, 1.0, 1)],
+                  ws)
+    pairs = REG.cpu().numpy()
+    phi = 0.0
+    for i in range(n_components):
+        for j in range(i + 1, n_components):
+            phi += pairs[i, j]
+    return 2.0 / (n_components * n_features * (n_components - 1.0)) * phi
+
+
+def _gpnh_cost(data, weights, dictionary, lambda_W=0):
+    """Evaluate GPNH convex coding cost function (gpnh_convex_coding.py:199-210)."""
+    torch = be.require_cuda()
+    data = np.asarray(data, dtype=np.float64)
+    n_samples, n_features = data.shape
+    k = weights.shape[1]
+    X = be.to_device_padded(data)
+    Z = be.to_device(weights)
+    WT = be.to_device_padded(np.ascontiguousarray(np.asarray(dictionary).T))
+    out = be.zeros(1)
+    part = be.zeros(n_samples)
+    be.check(be.library().cdr_residual_sq(
+        X.data_ptr(), X.stride(0), n_samples, n_features, Z.data_ptr(), k, WT.data_ptr(),
+        WT.stride(0), out.data_ptr(), part.data_ptr(), be.stream_ptr()), 'cdr_residual_sq')
+    cost = 0.5 * float(out.item()) / n_samples
+    if lambda_W != 0:
+        cost += lambda_W * _gpnh_regularization(dictionary)
+    return cost
+
+
+def _update_gpnh_dictionary(X, weights, ZtZ, GW, lambda_W=0):
+    """Update dictionary for GPNH regularized convex coding
+    (gpnh_convex_coding.py:213-226)."""
+    X = np.asarray(X, dtype=np.float64)
+    n_samples, n_features = X.shape
+    k = weights.shape[1]
+    # pinv(ZtZ/n + lambda GW) / n == pinv(ZtZ + n lambda GW)
+    lhs = be.to_device(np.asarray(ZtZ, dtype=np.float64) +
+                       n_samples * lambda_W * np.asarray(GW, dtype=np.float64))
+    P = be.zeros(k, k)
+    be.check(be.library().cdr_sym_pinv(lhs.data_ptr(), k, P.data_ptr(), None, be.stream_ptr()),
+             'cdr_sym_pinv')
+    Xd = be.to_device_padded(X)
+    Z = be.to_device(weights)
+    WT = be.zeros(k, Xd.stride(0))
+    ws = be.Workspace(n_samples, n_features, k)
+    be.reduce_samples(Z, 1, k, Xd, n_samples, n_features, k, WT, ws, E=P)
+    return be.to_host(WT, k, n_features).T
+
+
+def _update_gpnh_weights(X, weights, dictionary, **solver_kwargs):
+    """Update weights for GPNH regularized convex coding
+    (gpnh_convex_coding.py:254-279)."""
+    X = np.asarray(X, dtype=np.float64)
+    n_samples, n_features = X.shape
+    k = weights.shape[1]
+    params = be.make_spg_params(solver_kwargs)
+    Xd = be.to_device_padded(X)
+    Z = be.to_device(weights)
+    WT = be.to_device_padded(np.ascontiguousarray(np.asarray(dictionary).T))
+    ldt = be.round_up(n_samples)
+    XWt = be.zeros(k, ldt)
+    WtW = be.zeros(k, k)
+    ws = be.Workspace(n_samples, n_features, k)
+    be.reduce_features(WT, Xd, n_samples, n_features, k, XWt, ws)
+    ld = WT.stride(0)
+    be.small_gram([(WT, ld, 1, k, WT, ld, 1, k, n_features, WtW, 1.0, 0)], ws)
+    be.quad_simplex_spg_batched(WtW, None, XWt, 1, ldt, Z, n_samples, k, params)
+    return be.to_host(Z)
+
+
+def _iterate_gpnh_convex_coding(X, weights, dictionary, lambda_W=0,
+                                update_weights=True, update_dictionary=True,
+                                tolerance=1e-6, max_iterations=1000, verbose=0,
+                                **kwargs):
+    """Iteratively update weights and dictionary until convergence is reached.
+
+    Returns ``(weights, dictionary, cost, n_iter, avg_time_per_iter, cost_deltas)``
+    exactly like gpnh_convex_coding.py:282-402.  ``trace_XtX`` may be passed to
+    skip the initial ||X||_F^2 reduction.
+    """
+    if kwargs.get('dictionary_solver_kwargs', {}):
+        # _update_gpnh_dictionary takes no solver options (gpnh_convex_coding.py:213, :348-350)
+        raise TypeError("_update_gpnh_dictionary() got an unexpected keyword argument '%s'"
+                        % next(iter(kwargs['dictionary_solver_kwargs'])))
+    X = np.asarray(X, dtype=np.float64)
+    engine = _GpnhEngine(
+        X, weights, dictionary, lambda_W=lambda_W, tolerance=tolerance,
+        max_iterations=max_iterations,
+        stopping_criterion=kwargs.get('stopping_criterion', 'abs_delta_f'),
+        require_monotonic_cost_decrease=kwargs.get('require_monotonic_cost_decrease', True),
+        weights_solver_kwargs=kwargs.get('weights_solver_kwargs', {}),
+        update_dictionary=update_dictionary, update_weights=update_weights,
+        trace_XtX=kwargs.get('trace_XtX'), X_device=kwargs.get('X_device'))
+    engine.run(verbose=verbose)
+    new_weights = engine.weights() if update_weights else weights
+    new_dictionary = engine.dictionary() if update_dictionary else dictionary
+    return (new_weights, new_dictionary, engine.cost, engine.n_iter,
+            engine.avg_time_per_iter, engine.cost_deltas)
+
+
+def _initialize_gpnh_convex_coding_dictionary(data, n_components, init='random',
+                                              random_state=None, **kwargs):
+    """gpnh_convex_coding.py:41-81, 93-115."""
+    if init is None:
+        init = 'random'
+    rng = check_random_state(random_state)
+    n_samples, n_features = data.shape
+    if init == 'random':
+        avg = np.sqrt(np.abs(data).mean() / n_components)
+        return avg * rng.randn(n_features, n_components)
+    if init == 'furthest_sum':
+        start_index = kwargs.get('start_index', None)
+        n_extra_steps = kwargs.get('n_extra_steps', 10)
+        exclude = kwargs.get('exclude', None)
+        if start_index is None:
+            start_index = rng.randint(n_samples)
+        if exclude is None:
+            exclude = np.array([], dtype='i8')
+        Xd = be.to_device_padded(data)
+        K = be.gram(Xd, n_samples, n_features)
+        D = dissimilarity_from_gram_device(K, n_samples)
+        selected = furthest_sum_device(D, n_samples, n_components, start_index, exclude,
+                                       n_extra_steps)
+        dictionary = np.zeros((n_features, n_components), dtype=np.float64)
+        for i in range(n_components):
+            dictionary[:, i] = data[selected[i]]
+        return dictionary
+    raise ValueError('Invalid init parameter: got %r instead of one of %r' %
+                     (init, INITIALIZATION_METHODS))
+
+
+def _initialize_gpnh_convex_coding_weights(data, n_components, init='random',
+                                           random_state=None):
+    """gpnh_convex_coding.py:84-90, 118-129."""
+    if init is None:
+        init = 'random'
+    if init in ('furthest_sum', 'random'):
+        rng = check_random_state(random_state)
+        return right_stochastic_matrix((data.shape[0], n_components), random_state=rng)
+    raise ValueError('Invalid init parameter: got %r instead of one of %r' %
+                     (init, INITIALIZATION_METHODS))
+
+
+def _initialize_gpnh_convex_coding(data, n_components, init='random',
+                                   random_state=None, **kwargs):
+    """Dictionary first, then weights: the RNG draw order of gpnh_convex_coding.py:132-143."""
+    rng = check_random_state(random_state)
+    dictionary = _initialize_gpnh_convex_coding_dictionary(
+        data, n_components, init=init, random_state=rng, **kwargs)
+    weights = _initialize_gpnh_convex_coding_weights(
+        data, n_components, init=init, random_state=rng)
+    return dictionary, weights
+
+
+class GPNHConvexCoding():
+    """Convex encoding of data with GPNH regularization.
+
+    Drop-in for the reference class (gpnh_convex_coding.py:405-668): same
+    constructor, ``fit`` / ``fit_transform`` / ``transform`` /
+    ``inverse_transform`` and the attributes ``weights``, ``dictionary``,
+    ``cost``, ``n_iter``, ``avg_time_per_iter``, ``cost_deltas``.
+    """
+
+    def __init__(self, n_components, lambda_W=0, init=None, tolerance=1e-6,
+                 max_iterations=1000, verbose=0, random_state=None, **kwargs):
+        self.n_components = n_components
+        self.lambda_W = lambda_W
+        self.init = init
+        self.tolerance = tolerance
+        self.max_iterations = max_iterations
+        self.verbose = verbose
+        self.random_state = check_random_state(random_state)
+        self.require_monotonic_cost_decrease = kwargs.get(
+            'require_monotonic_cost_decrease', True)
+        self.stopping_criterion = kwargs.get('stopping_criterion', 'abs_delta_f')
+        self.weights = None
+        self.dictionary = None
+        self.cost = 0
+        self.n_iter = 0
+        self.avg_time_per_iter = 0
+        self.cost_deltas = None
+        self.weights_solver_kwargs = kwargs.get('weights_solver_kwargs', {})
+        self.dictionary_solver_kwargs = kwargs.get('dictionary_solver_kwargs', {})
+
+    def _check_params(self, n_features):
+        if self.n_components is None:
+            self.n_components = n_features
+        if not isinstance(self.n_components, INTEGER_TYPES) or self.n_components <= 0:
+            raise ValueError('Number of components must be a positive integer;'
+                             ' got (n_components=%r)' % self.n_components)
+        if not isinstance(self.max_iterations, INTEGER_TYPES) or self.max_iterations <= 0:
+            raise ValueError('Maximum number of iterations must be a positive '
+                             'integer; got (max_iterations=%r)' % self.max_iterations)
+        if not isinstance(self.tolerance, numbers.Number) or self.tolerance < 0:
+            raise ValueError('Tolerance for stopping criteria must be '
+                             'positive; got (tolerance=%r)' % self.tolerance)
+
+    def _gpnh_convex_coding(self, data, dictionary=None, weights=None,
+                            update_dictionary=True, update_weights=True, **kwargs):
+        """Calculate GPNH-regularized convex coding of dataset
+        (gpnh_convex_coding.py:501-572)."""
+        n_samples, n_features = data.shape
+        self._check_params(n_features)
+        k = self.n_components
+        if self.init == 'custom':
+            _check_init_weights(weights, (n_samples, k), '_gpnh_convex_coding (input weights)')
+            _check_init_dictionary(dictionary, (n_features, k),
+                                   '_gpnh_convex_coding (input dictionary)')
+        elif not update_dictionary and update_weights:
+            _check_init_dictionary(dictionary, (n_features, k),
+                                   '_gpnh_convex_coding (input dictionary)')
+            weights = _initialize_gpnh_convex_coding_weights(
+                data, k, init=self.init, random_state=self.random_state)
+        elif update_dictionary and not update_weights:
+            _check_init_weights(weights, (n_samples, k), '_gpnh_convex_coding (input weights)')
+            dictionary = _initialize_gpnh_convex_coding_dictionary(
+                data, k, init=self.init, random_state=self.random_state, **kwargs)
+        else:
+            dictionary, weights = _initialize_gpnh_convex_coding(
+                data, k, init=self.init, random_state=self.random_state, **kwargs)
+
+        self.weights = np.array(weights, dtype=np.float64)
+        self.dictionary = np.array(dictionary, dtype=np.float64)
+
+        self.weights, self.dictionary, cost, n_iter, avg_time_per_iter, cost_deltas = \
+            _iterate_gpnh_convex_coding(
+                data, self.weights, self.dictionary, lambda_W=self.lambda_W,
+                update_dictionary=update_dictionary, update_weights=update_weights,
+                tolerance=self.tolerance, max_iterations=self.max_iterations,
+                verbose=self.verbose,
+                require_monotonic_cost_decrease=self.require_monotonic_cost_decrease,
+                stopping_criterion=self.stopping_criterion,
+                weights_solver_kwargs=self.weights_solver_kwargs,
+                dictionary_solver_kwargs=self.dictionary_solver_kwargs)
+
+        if n_iter == self.max_iterations and self.tolerance > 0:
+            warnings.warn('Maximum number of iterations %d reached.' %
+                          self.max_iterations, UserWarning)
+        return cost, n_iter, avg_time_per_iter, cost_deltas
+
+    def fit_transform(self, data, dictionary=None, weights=None, **kwargs):
+        """Fit convex coding and return transformed data
+        (gpnh_convex_coding.py:574-603)."""
+        data = np.asarray(data)
+        cost_, n_iter_, avg_time_per_iter_, cost_deltas_ = self._gpnh_convex_coding(
+            data, dictionary=dictionary, weights=weights, **kwargs)
+        self.cost = cost_
+        self.n_iter = n_iter_
+        self.avg_time_per_iter = avg_time_per_iter_
+        self.cost_deltas = cost_deltas_
+        return self.weights
+
+    def fit(self, data, **kwargs):
+        """Fit convex coding to data."""
+        self.fit_transform(data, **kwargs)
+        return self
+
+    def transform(self, data):
+        """Transform the data according to the fitted factorization
+        (gpnh_convex_coding.py:623-652): weights-only run with a fresh random start."""
+        data = np.asarray(data)
+        cost_ = self._gpnh_convex_coding(
+            data=data, dictionary=self.dictionary,
+            update_dictionary=False, update_weights=True)[0]
+        return self.weights, cost_
+
+    def inverse_transform(self, weights):
+        """Transform data back into its original space."""
+        return weights.dot(self.dictionary.T)

@@ -1,0 +1,260 @@
+"""k-means (Lloyd) with FurthestSum initialisation.
+
+The reference has no k-means of its own: its drivers call
+``sklearn.cluster.KMeans`` (``bin/run_hadisst_kmeans.py:128-131``,
+``bin/run_jra55_kmeans.py:115-132``).  This module restates the Lloyd path of
+scikit-learn 1.9.0 (``sklearn/cluster/_kmeans.py``, ``_k_means_lloyd.pyx``,
+``_k_means_common.pyx``) on the GPU: data centring, tolerance scaling,
+first-minimum assignment, centre update, empty-cluster relocation, the
+label-equality / centre-shift stopping rule and the final E-step.  The two
+passes over the data per iteration are the streaming contractions
+``cdr_reduce_features`` (x.c for all samples and centres) and
+``cdr_reduce_samples`` (per-cluster sums through a one-hot matrix).
+"""
+
+import numpy as np
+from sklearn.utils import check_random_state
+
+from . import _backend as be
+from .furthest_sum import dissimilarity_from_gram_device, furthest_sum_device
+
+
+def furthest_sum_centres(X, n_clusters, start_index, extra_steps=10, exclude=None):
+    """Indices of the FurthestSum picks on the rows of X (distances from the Gram matrix,
+    as the estimators build them: archetypal_analysis.py:96-100)."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    T, d = X.shape
+    Xd = be.to_device_padded(X)
+    K = be.gram(Xd, T, d)
+    D = dissimilarity_from_gram_device(K, T)
+    return furthest_sum_device(D, T, n_clusters, start_index, exclude, extra_steps)
+
+
+def kmeans_lloyd(X, init_centres, tol=1e-4, max_iter=300, verbose=False):
+    """``KMeans(init=init_centres, n_init=1, algorithm='lloyd').fit(X)``.
+
+    Returns ``(labels int32[T], centres k x d, inertia, n_iter)``.
+    """
+    torch = be.require_cuda()
+    lib = be.library()
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    init_centres = np.ascontiguousarray(init_centres, dtype=np.float64)
+    T, d = X.shape
+    k = init_centres.shape[0]
+    if k > be.MAX_COMPONENTS:
+        raise ValueError('n_clusters > %d is not supported by the B200 build' % be.MAX_COMPONENTS)
+    s = be.stream_ptr
+    Xd = be.to_device_padded(X)
+    ldx = Xd.stride(0)
+    ldt = be.round_up(T)
+
+    # _kmeans.py:285-294 (tolerance) and :1486-1493 (centring); NumPy's row-sequential order
+    mean = be.zeros(ldx)
+    var = be.zeros(ldx)
+    be.check(lib.cdr_column_moments(Xd.data_ptr(), ldx, T, d, mean.data_ptr(), var.data_ptr(), s()),
+             'cdr_column_moments')
+    tol_abs = float(np.mean(var[:d].cpu().numpy()) * tol)
+    be.check(lib.cdr_center_columns(Xd.data_ptr(), ldx, T, d, mean.data_ptr(), -1.0, s()),
+             'cdr_center_columns')
+    centres = be.to_device_padded(init_centres)
+    be.check(lib.cdr_center_columns(centres.data_ptr(), ldx, k, d, mean.data_ptr(), -1.0, s()),
+             'cdr_center_columns')
+
+    labels = torch.full((T,), -1, dtype=torch.int32, device='cuda')
+    onehot = be.zeros(k, ldt)
+    xct = be.zeros(k, ldt)
+    sums = be.zeros(k, ldx)
+    cnorm = be.zeros(k)
+    shift = be.zeros(k)
+    dist = be.zeros(T)
+    counts = torch.zeros(k, dtype=torch.int32, device='cuda')
+    changed = torch.zeros(1, dtype=torch.int32, device='cuda')
+    ws = be.Workspace(T, d, k)
+
+    def e_step():
+        be.check(lib.cdr_row_sqnorms(centres.data_ptr(), ldx, k, d, cnorm.data_ptr(), s()),
+                 'cdr_row_sqnorms')
+        be.reduce_features(centres, Xd, T, d, k, xct, ws)
+        counts.zero_()
+        changed.zero_()
+        be.check(lib.cdr_kmeans_labels(xct.data_ptr(), ldt, cnorm.data_ptr(), T, k,
+                                       labels.data_ptr(), onehot.data_ptr(), ldt,
+                                       counts.data_ptr(), changed.data_ptr(), s()),
+                 'cdr_kmeans_labels')
+
+    def sq_distances():
+        be.check(lib.cdr_kmeans_sqdist(Xd.data_ptr(), ldx, T, d, centres.data_ptr(), ldx,
+                                       labels.data_ptr(), dist.data_ptr(), s()),
+                 'cdr_kmeans_sqdist')
+
+    strict = False
+    n_iter = 0
+    for it in range(max_iter):
+        n_iter = it + 1
+        e_step()
+        be.reduce_samples(onehot, ldt, 1, Xd, T, d, k, sums, ws)
+        weights = counts.to(torch.float64)
+        host_counts = counts.cpu().numpy()
+        if (host_counts == 0).any():
+            # _k_means_common.pyx:167-212 (rare): move empty clusters onto the samples
+            # farthest from their current centres
+            empty = np.where(host_counts == 0)[0]
+            sq_distances()
+            dh = dist.cpu().numpy()
+            if np.max(dh) != 0:
+                far = np.argpartition(dh, -empty.size)[:-empty.size - 1:-1]
+                lab = labels.cpu().numpy()
+                for idx, cid in enumerate(empty):
+                    far_idx = int(far[idx])
+                    old = int(lab[far_idx])
+                    sums[old, :] -= Xd[far_idx, :]
+                    sums[int(cid), :] = Xd[far_idx, :]
+                    weights[int(cid)] = 1.0
+                    weights[old] -= 1.0
+        be.check(lib.cdr_kmeans_update(sums.data_ptr(), ldx, weights.data_ptr(),
+                                       centres.data_ptr(), ldx, k, d, shift.data_ptr(), s()),
+                 'cdr_kmeans_update')
+        moved = int(changed.item())
+        if not moved:
+            strict = True
+            break
+        sh = shift.cpu().numpy()
+        shift_tot = float((np.sqrt(sh) ** 2).sum())      # _kmeans.py:733: (center_shift**2).sum()
+        if verbose:
+            print('Iteration %d, center shift %.6e' % (it, shift_tot))
+        if shift_tot <= tol_abs:
+            break
+    if not strict:
+        e_step()                                         # _kmeans.py:745-757
+    sq_distances()
+    total = be.zeros(1)
+    be.check(lib.cdr_sum_vector(dist.data_ptr(), T, total.data_ptr(), s()), 'cdr_sum_vector')
+    inertia = float(total.item())
+    be.check(lib.cdr_center_columns(centres.data_ptr(), ldx, k, d, mean.data_ptr(), 1.0, s()),
+             'cdr_center_columns')
+    return (labels.cpu().numpy(), be.to_host(centres, k, d), inertia, n_iter)
+
+
+class KMeans():
+    """Minimal estimator around :func:`kmeans_lloyd` with the scikit-learn attribute
+    names the reference's drivers read (``cluster_centers_``, ``labels_``, ``inertia_``,
+    ``n_iter_``; bin/run_hadisst_kmeans.py:128-137).
+
+    ``init`` is an explicit (n_clusters, n_features) array, ``'furthest_sum'`` (start
+    index drawn from ``random_state``, 10 replacement passes) or ``'random'`` (distinct
+    random samples).  With ``n_init > 1`` the run with the lowest inertia is kept.
+    """
+
+    def __init__(self, n_clusters=8, init='furthest_sum', n_init=1, max_iter=300, tol=1e-4,
+                 verbose=0, random_state=None, extra_steps=10):
+        self.n_clusters = n_clusters
+        self.init = init
+        self.n_init = n_init
+        self.max_iter = max_iter
+        self.tol = tol
+        self.verbose = verbose
+        self.random_state = random_state
+        self.extra_steps = extra_steps
+
+    def _initial_centres(self, X, rng):
+        if isinstance(self.init, str):
+            if self.init == 'furthest_sum':
+                start = rng.randint(X.shape[0])
+                picks = furthest_sum_centres(X, self.n_clusters, start, self.extra_steps)
+                return X[picks].copy()
+            if self.init == 'random':
+                picks = rng.permutation(X.shape[0])[:self.n_clusters]
+                return X[picks].copy()
+            raise ValueError("init must be an array, 'furthest_sum' or 'random'; got %r"
+                             % self.init)
+        init = np.asarray(self.init, dtype=np.float64)
+        if init.shape != (self.n_clusters, X.shape[1]):
+            raise ValueError('The shape of the initial centers %s does not match the number '
+                             'of clusters %d and features %d' %
+                             (init.shape, self.n_clusters, X.shape[1]))
+        return init
+
+    def fit(self, X, y=None):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        rng = check_random_state(self.random_state)
+        n_init = 1 if not isinstance(self.init, str) else max(1, int(self.n_init))
+        best = None
+        for _ in range(n_init):
+            centres0 = self._initial_centres(X, rng)
+            result = kmeans_lloyd(X, centres0, tol=self.tol, max_iter=self.max_iter,
+                                  verbose=bool(self.verbose))
+            if best is None or result[2] < best[2]:
+                best = result
+        self.labels_, self.cluster_centers_, self.inertia_, self.n_iter_ = best
+        return self
+
+    def fit_predict(self, X, y=None):
+        return self.fit(X).labels_
+
+    def predict(self, X):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        labels, _, _, _ = _assign_only(X, self.cluster_centers_)
+        return labels
+
+
+def _assign_only(X, centres):
+    """Labels of X for fixed centres (one E-step)."""
+    torch = be.require_cuda()
+    lib = be.library()
+    T, d = X.shape
+    k = centres.shape[0]
+    Xd = be.to_device_padded(X)
+    Cd = be.to_device_padded(np.ascontiguousarray(centres, dtype=np.float64))
+    ldx, ldt = Xd.stride(0), be.round_up(T)
+    labels = torch.full((T,), -1, dtype=torch.int32, device='cuda')
+    onehot = be.zeros(k, ldt)
+    xct = be.zeros(k, ldt)
+    cnorm = be.zeros(k)
+    counts = torch.zeros(k, dtype=torch.int32, device='cuda')
+    changed = torch.zeros(1, dtype=torch.int32, device='cuda')
+    ws = be.Workspace(T, d, k)
+    be.check(lib.cdr_row_sqnorms(Cd.data_ptr(), ldx, k, d, cnorm.data_ptr(), be.stream_ptr()),
+             'cdr_row_sqnorms')
+    be.reduce_features(Cd, Xd, T, d, k, xct, ws)
+    be.check(lib.cdr_kmeans_labels(xct.data_ptr(), ldt, cnorm.data_ptr(), T, k, labels.data_ptr(),
+                                   onehot.data_ptr(), ldt, counts.data_ptr(), changed.data_ptr(),
+                                   be.stream_ptr()), 'cdr_kmeans_labels')
+    return labels.cpu().numpy(), None, None, None
+
+
+def gap_statistic(X, n_clusters, n_trials=100, n_init=10, reference='pca',
+                  random_state=None, **kwargs):
+    """Gap statistic of Tibshirani et al. around this module's k-means
+    (reference kmeans.py:81-108; model selection, outside the alternating-update path).
+
+    Returns ``(gap, standard_error)``.  Reference data are drawn uniformly from the
+    bounding box of X ('uniform') or of X rotated onto its principal axes ('pca').
+    """
+    rng = check_random_state(random_state)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+
+    def dispersion(data):
+        model = KMeans(n_clusters=n_clusters, init='random', n_init=n_init, random_state=rng,
+                       **kwargs).fit(data)
+        return np.log(model.inertia_)
+
+    if reference not in ('uniform', 'pca'):
+        raise ValueError("invalid reference distribution '%s'" % reference)
+    log_w = dispersion(X)
+    centred = X - X.mean(axis=0)
+    if reference == 'pca':
+        _, _, vt = np.linalg.svd(centred, full_matrices=False)
+        rotated = centred.dot(vt.T)
+    else:
+        vt = None
+        rotated = X
+    lo, hi = rotated.min(axis=0), rotated.max(axis=0)
+    ref_log_w = np.empty(n_trials)
+    for i in range(n_trials):
+        sample = rng.uniform(lo, hi, size=rotated.shape)
+        if vt is not None:
+            sample = sample.dot(vt) + X.mean(axis=0)
+        ref_log_w[i] = dispersion(sample)
+    gap = ref_log_w.mean() - log_w
+    sk = np.sqrt(1.0 + 1.0 / n_trials) * ref_log_w.std()
+    return gap, sk

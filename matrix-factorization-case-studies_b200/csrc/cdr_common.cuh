@@ -1,0 +1,146 @@
+// Shared device/host helpers for the convex_dim_red B200 kernels (sm_100a).
+//
+// Everything here is internal to the shared library; the public surface is
+// include/cdr_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/cdr_b200.h"
+
+#define CDR_FULL_MASK 0xffffffffu
+
+// Launch-error check used by every C-ABI entry point (no synchronisation:
+// all entry points are asynchronous on the caller's stream).
+// Also counts kernel launches (cdr_launch_count): the macro follows every <<<>>>.
+extern unsigned long long cdr_g_kernel_launches;
+#define CDR_RETURN_IF_LAUNCH_FAILED()                         \
+    do {                                                      \
+        cudaError_t e__ = cudaGetLastError();                 \
+        if (e__ != cudaSuccess) return (int)e__;              \
+        ++cdr_g_kernel_launches;                              \
+    } while (0)
+
+#define CDR_CHECK_ARG(cond)                                   \
+    do {                                                      \
+        if (!(cond)) return CDR_ERR_INVALID_ARGUMENT;         \
+    } while (0)
+
+namespace cdr {
+
+__device__ __forceinline__ bool is_done(const cdr_flags* flags)
+{
+    // Every kernel of an iteration checks this first: once the on-device
+    // convergence / error test has fired, the rest of a captured CUDA graph
+    // degenerates to empty launches and the state is left untouched.
+    return flags != nullptr && *((volatile const int*)&flags->done) != 0;
+}
+
+// --------------------------------------------------------------------------
+// warp / block reductions (fixed order => deterministic results)
+// --------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(CDR_FULL_MASK, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(CDR_FULL_MASK, v, o));
+    return v;
+}
+
+__device__ __forceinline__ int warp_sum_int(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(CDR_FULL_MASK, v, o);
+    return v;
+}
+
+// Block-wide sum of up to N values per thread.  `scratch` must hold
+// N * 32 doubles.  All threads receive the result.  blockDim.x must be a
+// multiple of 32 and <= 1024.
+template <int N>
+__device__ __forceinline__ void block_sum(double (&v)[N], double* scratch)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
+    __syncthreads();                      // scratch may still be read from a previous call
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) scratch[i * 32 + warp] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double x = (lane < nwarps) ? scratch[i * 32 + lane] : 0.0;
+        v[i] = warp_sum(x);
+    }
+}
+
+__device__ __forceinline__ double block_max(double v, double* scratch)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    double x = (lane < nwarps) ? scratch[lane] : -INFINITY;
+    return warp_max(x);
+}
+
+// --------------------------------------------------------------------------
+// fp64 tensor-core tile: D(8x8) += A(8x4, row) * B(4x8, col).  SASS: DMMA.8x8x4
+//   a : A[lane>>2][lane&3]        b : B[lane&3][lane>>2]
+//   c0, c1 : C[lane>>2][2*(lane&3) + {0,1}]
+// --------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
+{
+    asm volatile(
+        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double2 ldg_nc_d2(const double* p)
+{
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];\n"
+                 : "=d"(v.x), "=d"(v.y)
+                 : "l"(p));
+    return v;
+}
+
+// --------------------------------------------------------------------------
+// SPG scalar helpers (reference spg.py:19-43)
+// --------------------------------------------------------------------------
+__host__ __device__ __forceinline__ double spg_step_length(double lam, double delta,
+                                                           double f_old, double f_new,
+                                                           double sigma_one, double sigma_two)
+{
+    // spg.py:23-31: safeguarded quadratic interpolation; note the lower
+    // safeguard sigma_one is absolute, not relative to lam.
+    const double cand = -0.5 * lam * lam * delta / (f_new - f_old - lam * delta);
+    if (sigma_one <= cand && cand <= sigma_two * lam) return cand;
+    return 0.5 * lam;
+}
+
+__host__ __device__ __forceinline__ double spg_cauchy_step(double beta, double sksk,
+                                                           double alpha_min, double alpha_max)
+{
+    // spg.py:36-43
+    if (beta <= 0.0) return alpha_max;
+    return fmin(alpha_max, fmax(alpha_min, sksk / beta));
+}
+
+static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace cdr

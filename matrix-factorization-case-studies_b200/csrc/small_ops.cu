@@ -1,0 +1,392 @@
+// Small dense pieces around the streaming passes: k x k products reduced over a
+// long axis (Z'Z, C K C', W'W, ...), the k x k pseudo-inverse of the GPNH
+// dictionary step and the scalar cost bookkeeping of the outer loops.
+#include "cdr_common.cuh"
+
+namespace cdr {
+
+// ======================================================================
+// batched small products
+// ======================================================================
+constexpr int kGramMaxBlocks = 128;
+constexpr int kGramTile = 32;
+constexpr int kGramMaxPairs = CDR_MAX_COMPONENTS * CDR_MAX_COMPONENTS;
+
+struct GramBatch {
+    cdr_small_gram_desc d[CDR_GRAM_BATCH];
+    int nblk[CDR_GRAM_BATCH];
+};
+
+// partial[desc][blk][pair]
+__global__ void __launch_bounds__(256)
+small_gram_partial_kernel(GramBatch batch, double* __restrict__ part, const cdr_flags* flags)
+{
+    if (is_done(flags)) return;
+    const cdr_small_gram_desc& ds = batch.d[blockIdx.y];
+    const int nblk = batch.nblk[blockIdx.y];
+    if ((int)blockIdx.x >= nblk) return;
+    __shared__ double As[CDR_MAX_COMPONENTS][kGramTile + 1];
+    __shared__ double Bs[CDR_MAX_COMPONENTS][kGramTile + 1];
+
+    const int ka = ds.ka, kb = ds.kb, npairs = ka * kb;
+    int chunk = (ds.n + nblk - 1) / nblk;
+    chunk = (chunk + kGramTile - 1) / kGramTile * kGramTile;
+    const int n0 = blockIdx.x * chunk;
+    const int n1 = min(ds.n, n0 + chunk);
+
+    double acc[kGramMaxPairs / 256];
+#pragma unroll
+    for (int s = 0; s < kGramMaxPairs / 256; ++s) acc[s] = 0.0;
+
+    for (int nb = n0; nb < n1; nb += kGramTile) {
+        const int w = min(kGramTile, n1 - nb);
+        for (int idx = threadIdx.x; idx < ka * kGramTile; idx += 256) {
+            const int i = idx / kGramTile, cix = idx % kGramTile;
+            As[i][cix] = (cix < w) ? ds.A[(long)i * ds.sAi + (long)(nb + cix) * ds.sAn] : 0.0;
+        }
+        for (int idx = threadIdx.x; idx < kb * kGramTile; idx += 256) {
+            const int j = idx / kGramTile, cix = idx % kGramTile;
+            Bs[j][cix] = (cix < w) ? ds.B[(long)j * ds.sBj + (long)(nb + cix) * ds.sBn] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < kGramMaxPairs / 256; ++s) {
+            const int p = threadIdx.x + s * 256;
+            if (p < npairs) {
+                const int i = p / kb, j = p % kb;
+                double a = acc[s];
+                if (ds.mode == 0) {
+#pragma unroll 8
+                    for (int cix = 0; cix < kGramTile; ++cix) a = fma(As[i][cix], Bs[j][cix], a);
+                } else {
+#pragma unroll 8
+                    for (int cix = 0; cix < kGramTile; ++cix) {
+                        const double df = As[i][cix] - Bs[j][cix];
+                        a = fma(df, df, a);
+                    }
+                }
+                acc[s] = a;
+            }
+        }
+        __syncthreads();
+    }
+    double* dst = part + ((long)blockIdx.y * kGramMaxBlocks + blockIdx.x) * kGramMaxPairs;
+#pragma unroll
+    for (int s = 0; s < kGramMaxPairs / 256; ++s) {
+        const int p = threadIdx.x + s * 256;
+        if (p < npairs) dst[p] = acc[s];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+small_gram_final_kernel(GramBatch batch, const double* __restrict__ part, const cdr_flags* flags)
+{
+    if (is_done(flags)) return;
+    const cdr_small_gram_desc& ds = batch.d[blockIdx.x];
+    const int nblk = batch.nblk[blockIdx.x];
+    const int npairs = ds.ka * ds.kb;
+    for (int p = threadIdx.x; p < npairs; p += 256) {
+        const double* src = part + ((long)blockIdx.x * kGramMaxBlocks) * kGramMaxPairs + p;
+        double s = 0.0;
+        for (int b = 0; b < nblk; ++b) s += src[(long)b * kGramMaxPairs];   // fixed order
+        ds.out[p] = ds.scale * s;
+    }
+}
+
+// ======================================================================
+// GPNH dictionary step: P = pinv(ZtZ / T + lambda * G_W) / T
+// ======================================================================
+// One CTA; cyclic Jacobi eigen-decomposition with a round-robin (parallel)
+// ordering: k/2 disjoint rotations per round.  The pseudo-inverse drops
+// eigenvalues below eps * k * max|eig|, the cut-off numpy.linalg.lstsq applies
+// with rcond=None (gpnh_convex_coding.py:224).
+constexpr int kJacLd = CDR_MAX_COMPONENTS + 1;
+
+__global__ void __launch_bounds__(256)
+gpnh_solve_matrix_kernel(const double* __restrict__ ZtZ, int k, double inv_n, double lambda_W,
+                         double gw_prefactor, double* __restrict__ P, const cdr_flags* flags)
+{
+    if (is_done(flags)) return;
+    extern __shared__ double jac_sm[];            // 2 * k * kJacLd doubles
+    double* A = jac_sm;
+    double* V = jac_sm + CDR_MAX_COMPONENTS * kJacLd;
+    __shared__ double rc[CDR_MAX_COMPONENTS / 2], rs[CDR_MAX_COMPONENTS / 2];
+    __shared__ int rp[CDR_MAX_COMPONENTS / 2], rq[CDR_MAX_COMPONENTS / 2];
+    __shared__ int rotated;
+    __shared__ double inv_eig[CDR_MAX_COMPONENTS];
+
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < k * k; idx += blockDim.x) {
+        const int i = idx / k, j = idx % k;
+        double v = ZtZ[idx] * inv_n;
+        if (k > 1) v += lambda_W * gw_prefactor * ((i == j ? (double)k : 0.0) - 1.0);
+        A[i * kJacLd + j] = v;
+        V[i * kJacLd + j] = (i == j) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+
+    const int kk = (k + 1) & ~1;        // even number of players
+    const int half = kk / 2;
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        if (tid == 0) rotated = 0;
+        __syncthreads();
+        for (int round = 0; round < kk - 1; ++round) {
+            if (tid < half) {
+                int a, b;
+                if (tid == 0) {
+                    a = kk - 1;
+                    b = round;
+                } else {
+                    a = (round + tid) % (kk - 1);
+                    b = (round - tid + (kk - 1)) % (kk - 1);
+                }
+                const int p = min(a, b), q = max(a, b);
+                double c = 1.0, s = 0.0;
+                if (q < k) {
+                    const double apq = A[p * kJacLd + q];
+                    const double app = A[p * kJacLd + p], aqq = A[q * kJacLd + q];
+                    if (apq != 0.0 && fabs(apq) > 2.220446049250313e-16 * sqrt(fabs(app * aqq))) {
+                        const double theta = (aqq - app) / (2.0 * apq);
+                        const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                        c = 1.0 / sqrt(t * t + 1.0);
+                        s = t * c;
+                        rotated = 1;
+                    }
+                }
+                rp[tid] = p;
+                rq[tid] = q;
+                rc[tid] = c;
+                rs[tid] = s;
+            }
+            __syncthreads();
+            // columns: A <- A J, V <- V J
+            for (int idx = tid; idx < half * k; idx += blockDim.x) {
+                const int m = idx / k, i = idx % k;
+                const int p = rp[m], q = rq[m];
+                if (q < k && rs[m] != 0.0) {
+                    const double c = rc[m], s = rs[m];
+                    const double aip = A[i * kJacLd + p], aiq = A[i * kJacLd + q];
+                    A[i * kJacLd + p] = c * aip - s * aiq;
+                    A[i * kJacLd + q] = s * aip + c * aiq;
+                    const double vip = V[i * kJacLd + p], viq = V[i * kJacLd + q];
+                    V[i * kJacLd + p] = c * vip - s * viq;
+                    V[i * kJacLd + q] = s * vip + c * viq;
+                }
+            }
+            __syncthreads();
+            // rows: A <- J' A
+            for (int idx = tid; idx < half * k; idx += blockDim.x) {
+                const int m = idx / k, j = idx % k;
+                const int p = rp[m], q = rq[m];
+                if (q < k && rs[m] != 0.0) {
+                    const double c = rc[m], s = rs[m];
+                    const double apj = A[p * kJacLd + j], aqj = A[q * kJacLd + j];
+                    A[p * kJacLd + j] = c * apj - s * aqj;
+                    A[q * kJacLd + j] = s * apj + c * aqj;
+                }
+            }
+            __syncthreads();
+        }
+        if (rotated == 0) break;
+        __syncthreads();
+    }
+
+    if (tid == 0) {
+        double emax = 0.0;
+        for (int i = 0; i < k; ++i) emax = fmax(emax, fabs(A[i * kJacLd + i]));
+        const double cut = 2.220446049250313e-16 * (double)k * emax;
+        for (int i = 0; i < k; ++i) {
+            const double e = A[i * kJacLd + i];
+            inv_eig[i] = (fabs(e) > cut) ? 1.0 / e : 0.0;
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < k * k; idx += blockDim.x) {
+        const int a = idx / k, b = idx % k;
+        double s = 0.0;
+        for (int i = 0; i < k; ++i) s = fma(V[a * kJacLd + i] * inv_eig[i], V[b * kJacLd + i], s);
+        P[idx] = s * inv_n;
+    }
+}
+
+// ======================================================================
+// GPNH cost bookkeeping (gpnh_convex_coding.py:352-399)
+// ======================================================================
+__device__ __forceinline__ bool cost_increased(double old_cost, double new_cost, double tol)
+{
+    // archetypal_analysis.py:167-174 / gpnh_convex_coding.py:146-153
+    return (new_cost > old_cost) && (fabs(new_cost - old_cost) > tol);
+}
+
+__device__ __forceinline__ bool stop_rule(int rule, double old_cost, double new_cost, double tol)
+{
+    // archetypal_analysis.py:177-197
+    const double delta = new_cost - old_cost;
+    if (rule == 0) return fabs(delta) < tol;
+    const double mx = fmax(fabs(new_cost), fabs(old_cost));
+    return fabs(delta / mx) < tol;
+}
+
+__device__ void finish_sub_step(cdr_loop_state* st, double* cost_deltas, double cost, int stage,
+                                int end_of_iteration)
+{
+    st->cost = cost;
+    if (stage == 0) return;                        // initial cost only
+    if (st->require_monotone && cost_increased(st->old_cost, cost, st->tolerance)) {
+        st->error_stage = stage;
+        st->done = 1;
+        return;
+    }
+    if (end_of_iteration) {
+        const int it = st->n_iter;
+        if (cost_deltas) cost_deltas[it] = cost - st->old_cost;
+        st->n_iter = it + 1;
+        if (stop_rule(st->stopping_rule, st->old_cost, cost, st->tolerance)) {
+            st->converged = 1;
+            st->done = 1;
+        } else if (it + 1 >= st->max_iterations) {
+            st->done = 1;
+        }
+    }
+}
+
+__global__ void loop_begin_kernel(cdr_loop_state* st)
+{
+    if (st->done) return;
+    if (st->n_iter >= st->max_iterations) {
+        st->done = 1;
+        return;
+    }
+    st->old_cost = st->cost;
+}
+
+__global__ void gpnh_cost_kernel(cdr_loop_state* st, double* cost_deltas,
+                                 const double* __restrict__ XWtZ, const double* __restrict__ ZtZ,
+                                 const double* __restrict__ WtW, const double* __restrict__ reg_pairs,
+                                 int k, int n_samples, int n_features, double lambda_W, int stage,
+                                 int end_of_iteration)
+{
+    if (st->done) return;
+    double tr1 = 0.0, tr2 = 0.0;
+    for (int i = 0; i < k; ++i) tr1 += XWtZ[i * k + i];
+    for (int i = 0; i < k; ++i)
+        for (int j = 0; j < k; ++j) tr2 += ZtZ[i * k + j] * WtW[j * k + i];
+    if (reg_pairs != nullptr) {
+        // gpnh_convex_coding.py:179-196
+        double phi = 0.0;
+        if (lambda_W != 0.0 && k > 1) {
+            for (int i = 0; i < k; ++i)
+                for (int j = i + 1; j < k; ++j) phi += reg_pairs[i * k + j];
+            phi *= 2.0 / ((double)k * (double)n_features * ((double)k - 1.0));
+        }
+        st->penalty = (lambda_W != 0.0) ? lambda_W * phi : 0.0;
+    }
+    const double cost = 0.5 * (st->trace_data - 2.0 * tr1 + tr2) / (double)n_samples + st->penalty;
+    finish_sub_step(st, cost_deltas, cost, stage, end_of_iteration);
+}
+
+}  // namespace cdr
+
+using namespace cdr;
+
+extern "C" size_t cdr_small_gram_workspace_bytes(void)
+{
+    return (size_t)CDR_GRAM_BATCH * kGramMaxBlocks * kGramMaxPairs * sizeof(double);
+}
+
+extern "C" int cdr_small_gram(const cdr_small_gram_desc* descs, int count, void* workspace,
+                              size_t workspace_bytes, const cdr_flags* flags, cdr_stream_t stream)
+{
+    CDR_CHECK_ARG(descs != nullptr && count >= 1 && count <= CDR_GRAM_BATCH);
+    if (workspace == nullptr || workspace_bytes < cdr_small_gram_workspace_bytes())
+        return CDR_ERR_WORKSPACE;
+    GramBatch batch;
+    int max_blk = 1;
+    for (int i = 0; i < count; ++i) {
+        batch.d[i] = descs[i];
+        CDR_CHECK_ARG(descs[i].ka >= 1 && descs[i].kb >= 1 && descs[i].n >= 0);
+        if (descs[i].ka > CDR_MAX_COMPONENTS || descs[i].kb > CDR_MAX_COMPONENTS)
+            return CDR_ERR_UNSUPPORTED;
+        int nb = (descs[i].n + 255) / 256;
+        if (nb < 1) nb = 1;
+        if (nb > kGramMaxBlocks) nb = kGramMaxBlocks;
+        batch.nblk[i] = nb;
+        if (nb > max_blk) max_blk = nb;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    small_gram_partial_kernel<<<dim3(max_blk, count), 256, 0, s>>>(batch, (double*)workspace, flags);
+    CDR_RETURN_IF_LAUNCH_FAILED();
+    small_gram_final_kernel<<<count, 256, 0, s>>>(batch, (const double*)workspace, flags);
+    CDR_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+extern "C" size_t cdr_sym_pinv_workspace_bytes(int k)
+{
+    (void)k;
+    return 0;
+}
+
+extern "C" int cdr_gpnh_solve_matrix(const double* ZtZ, int k, int n_samples, int n_features,
+                                     double lambda_W, double* P, void* workspace,
+                                     size_t workspace_bytes, const cdr_flags* flags,
+                                     cdr_stream_t stream)
+{
+    (void)workspace;
+    (void)workspace_bytes;
+    CDR_CHECK_ARG(k >= 1 && n_samples >= 1 && n_features >= 1);
+    if (k > CDR_MAX_COMPONENTS) return CDR_ERR_UNSUPPORTED;
+    // gpnh_convex_coding.py:296-300
+    const double pref = (k > 1) ? 4.0 / ((double)n_features * k * (k - 1)) : 0.0;
+    const size_t smem = 2 * (size_t)CDR_MAX_COMPONENTS * kJacLd * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gpnh_solve_matrix_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    gpnh_solve_matrix_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(
+        ZtZ, k, 1.0 / (double)n_samples, lambda_W, pref, P, flags);
+    CDR_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+extern "C" int cdr_sym_pinv(const double* S, int k, double* P, const cdr_flags* flags,
+                            cdr_stream_t stream)
+{
+    CDR_CHECK_ARG(k >= 1);
+    if (k > CDR_MAX_COMPONENTS) return CDR_ERR_UNSUPPORTED;
+    const size_t smem = 2 * (size_t)CDR_MAX_COMPONENTS * kJacLd * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gpnh_solve_matrix_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    gpnh_solve_matrix_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(S, k, 1.0, 0.0, 0.0, P, flags);
+    CDR_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+extern "C" int cdr_loop_begin(cdr_loop_state* state, cdr_stream_t stream)
+{
+    CDR_CHECK_ARG(state != nullptr);
+    loop_begin_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state);
+    CDR_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+extern "C" int cdr_gpnh_cost_check(cdr_loop_state* state, double* cost_deltas, const double* XWtZ,
+                                   const double* ZtZ, const double* WtW, const double* reg_pairs,
+                                   int k, int n_samples, int n_features, double lambda_W,
+                                   int stage, int end_of_iteration, cdr_stream_t stream)
+{
+    CDR_CHECK_ARG(state != nullptr && k >= 1);
+    gpnh_cost_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, cost_deltas, XWtZ, ZtZ, WtW,
+                                                        reg_pairs, k, n_samples, n_features,
+                                                        lambda_W, stage, end_of_iteration);
+    CDR_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}

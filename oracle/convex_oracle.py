@@ -552,6 +552,8 @@ def _aa_loop(apply_left, apply_right, trace_data, Z, C, alpha, delta,
         cost_deltas.append(new_cost - old_cost)
         if stop(old_cost, new_cost, tolerance):
             break
+    if kwargs.get('iter_times_out') is not None:
+        kwargs['iter_times_out'].extend(iter_times)      # bench.py's CPU arm
     return Z, C, alpha, new_cost, n_iter, float(np.mean(iter_times)), cost_deltas
 
 
@@ -718,6 +720,8 @@ def iterate_gpnh(X, Z, W, lambda_W=0, update_weights=True, update_dictionary=Tru
         cost_deltas.append(new_cost - old_cost)
         if stop(old_cost, new_cost, tolerance):
             break
+    if kwargs.get('iter_times_out') is not None:
+        kwargs['iter_times_out'].extend(iter_times)      # bench.py's CPU arm
     return Z, W, new_cost, n_iter, float(np.mean(iter_times)), cost_deltas
 
 

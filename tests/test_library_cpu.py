@@ -1,0 +1,154 @@
+"""CPU-side checks of the product package (no GPU needed): the shared library
+loads, exports every symbol ``include/cdr_b200.h`` declares, the ctypes struct
+mirrors match the C layouts, and the host-side logic (validation, RNG draw
+order, generic spg) behaves like the reference."""
+
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, PKG_DIR
+
+HEADER = os.path.join(ROOT, 'include', 'cdr_b200.h')
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from convex_dim_red import _backend as be
+    if not os.path.exists(be.LIB_PATH):
+        subprocess.check_call(['bash', os.path.join(PKG_DIR, 'csrc', 'build.sh')])
+    return be.library()
+
+
+def _declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    names = re.findall(r'\b(cdr_[a-z0-9_]+)\s*\(', text)
+    return sorted(set(names))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    from convex_dim_red import _backend as be
+    declared = _declared_functions()
+    assert len(declared) > 30
+    for name in declared:
+        assert hasattr(lib, name), 'symbol %s declared in cdr_b200.h is not exported' % name
+    missing = [n for n in declared if n not in be.SIGNATURES]
+    assert not missing, 'no ctypes signature for %s' % missing
+    extra = [n for n in be.SIGNATURES if n not in declared]
+    assert not extra, 'bound but not declared in the header: %s' % extra
+    assert b'sm_100a' in lib.cdr_version()
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    from convex_dim_red import _backend as be
+    src = tmp_path / 'sizes.c'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "cdr_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(cdr_spg_params),'
+                   'sizeof(cdr_loop_state), sizeof(cdr_small_gram_desc), sizeof(cdr_aa_buffers),'
+                   'offsetof(cdr_loop_state, tolerance), offsetof(cdr_aa_buffers, grad_scale));'
+                   'return 0;}\n')
+    exe = tmp_path / 'sizes'
+    subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    want = [ctypes.sizeof(be.SpgParams), ctypes.sizeof(be.LoopState),
+            ctypes.sizeof(be.SmallGramDesc), ctypes.sizeof(be.AaBuffers),
+            be.LoopState.tolerance.offset, be.AaBuffers.grad_scale.offset]
+    assert got == want
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    import convex_dim_red as cdr
+    from convex_dim_red import _backend as be
+    with pytest.raises(be.BackendError):
+        cdr.simplex_project_rows(np.ones((2, 3)))
+    with pytest.raises(be.BackendError):
+        cdr.GPNHConvexCoding(n_components=2, random_state=0).fit(np.ones((6, 4)))
+    with pytest.raises(be.BackendError):
+        cdr.furthest_sum(np.zeros((4, 4)), 2, 0)
+
+
+def test_product_package_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(PKG_DIR, 'convex_dim_red')):
+        for f in files:
+            if f.endswith('.py'):
+                text = open(os.path.join(dirpath, f)).read()
+                assert 'oracle' not in text.replace('convex_oracle', 'oracle') or \
+                    not re.search(r'^\s*(from|import)\s+oracle', text, flags=re.M), f
+
+
+def test_exports_match_reference_package():
+    import convex_dim_red as cdr
+    for name in ('ArchetypalAnalysis', 'KernelAA', 'GPNHConvexCoding', 'furthest_sum',
+                 'gap_statistic', 'simplex_project_rows', 'simplex_project_columns', 'spg',
+                 'left_stochastic_matrix', 'right_stochastic_matrix'):
+        assert hasattr(cdr, name)
+    from convex_dim_red.simplex_projection import simplex_project_vector      # noqa: F401
+    from convex_dim_red.archetypal_analysis import (                          # noqa: F401
+        _iterate_kernel_aa, _kernel_aa_cost, _update_kernel_aa_dictionary,
+        _update_kernel_aa_weights, _iterate_aa, _update_aa_dictionary)
+    from convex_dim_red.gpnh_convex_coding import (                           # noqa: F401
+        _gpnh_cost, _iterate_gpnh_convex_coding, _update_gpnh_dictionary, _update_gpnh_weights)
+
+
+def test_stochastic_matrices_draw_order():
+    import convex_dim_red as cdr
+    rs = np.random.RandomState(0)
+    ref = np.random.RandomState(0)
+    a = cdr.right_stochastic_matrix((4, 7), random_state=rs)
+    b = cdr.left_stochastic_matrix((5, 3), random_state=rs)
+    u = ref.uniform(size=(4, 7))
+    np.testing.assert_array_equal(a, u / u.sum(axis=1)[:, None])
+    v = ref.uniform(size=(5, 3))
+    np.testing.assert_array_equal(b, v / v.sum(axis=0)[None, :])
+    np.testing.assert_allclose(a.sum(axis=1), 1.0, atol=1e-15)
+    np.testing.assert_allclose(b.sum(axis=0), 1.0, atol=1e-15)
+
+
+def test_generic_spg_matches_golden(golden):
+    # reference tests/test_spg.py:37-90 and the golden box-constrained problem
+    import convex_dim_red as cdr
+    x, fx, n_it, n_fe = cdr.spg(lambda x: x ** 4 + 2 * x ** 2 + 1, lambda x: 4 * x ** 3 + 4 * x,
+                                0.4, project=lambda x: min(max(x, -1.0), 0.5))
+    np.testing.assert_allclose([x, fx, n_it, n_fe], golden['spg/quartic/out'], rtol=1e-12,
+                               atol=1e-14)
+    assert abs(x) < 1e-6 and abs(fx - 1) < 1e-6
+    M, y, x0 = golden['spg/box/M'], golden['spg/box/y'], golden['spg/box/x0']
+    x, fx, n_it, n_fe = cdr.spg(lambda v: 0.5 * (M.dot(v) - y).dot(M.dot(v) - y),
+                                lambda v: M.T.dot(M.dot(v) - y), x0,
+                                project=lambda v: np.fmin(np.fmax(v, 0.0), 0.3))
+    np.testing.assert_allclose(x, golden['spg/box/x'], rtol=1e-9)
+    np.testing.assert_allclose([fx, n_it, n_fe], golden['spg/box/stats'], rtol=1e-12)
+    # unconstrained scalar quadratic (tests/test_spg.py:13-35 style)
+    x, fx, _, _ = cdr.spg(lambda x: (x - 2.0) ** 2, lambda x: 2 * (x - 2.0), 10.0)
+    assert abs(x - 2.0) < 1e-6 and fx < 1e-10
+
+
+def test_validation_utils():
+    from convex_dim_red.validation_utils import (check_array_shape, check_stochastic_matrix,
+                                                 check_unit_axis_sums)
+    good = np.full((3, 4), 0.25)
+    check_stochastic_matrix(good, (3, 4), 'test', axis=1)
+    with pytest.raises(ValueError):
+        check_array_shape(good, (4, 3), 'test')
+    with pytest.raises(ValueError):
+        check_unit_axis_sums(good, 'test', axis=0)
+
+
+def test_solver_option_defaults():
+    from convex_dim_red import _backend as be
+    p = be.make_spg_params({})
+    assert (p.gamma, p.memory, p.sigma_one, p.sigma_two) == (1e-4, 1, 0.1, 0.9)
+    assert (p.max_iterations, p.max_feval, p.alpha0) == (1000, 2000, -1.0)
+    from convex_dim_red.archetypal_analysis import _dictionary_params
+    p = _dictionary_params({'max_iterations': 1})
+    assert (p.max_iterations, p.max_feval) == (1, 1000000)
+    with pytest.raises(ValueError):
+        be.make_spg_params({'memory': 99})

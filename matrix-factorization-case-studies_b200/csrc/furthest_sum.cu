@@ -37,6 +37,7 @@ struct FsState {
     int T;
     double* dist;   // running sums, T
     int* inlist;    // candidate still in the list, T
+    int* pos;       // original list position (index; T + n for the n-th appended candidate)
     double* H;      // H[event][candidate]
 };
 
@@ -49,7 +50,7 @@ __device__ bool fs_after(const FsState& s, int a, int b, int ev)
         const double ha = s.H[(long)e * s.T + a], hb = s.H[(long)e * s.T + b];
         if (ha != hb) return ha > hb;
     }
-    return a > b;
+    return s.pos[a] > s.pos[b];
 }
 
 __device__ int fs_pick(const FsState& s, int ev, int* sh_best)
@@ -84,16 +85,17 @@ __device__ int fs_pick(const FsState& s, int ev, int* sh_best)
 __global__ void __launch_bounds__(1024)
 furthest_sum_kernel(const double* __restrict__ D, long ldd, int T, int k, int start,
                     const int64_t* __restrict__ exclude, int n_exclude, int extra_steps,
-                    int64_t* selected, double* dist, int* inlist, double* H)
+                    int64_t* selected, double* dist, int* inlist, int* pos, double* H)
 {
     __shared__ int sh_best[33];
-    FsState s{D, ldd, T, dist, inlist, H};
+    FsState s{D, ldd, T, dist, inlist, pos, H};
 
     // furthest_sum.py:79-100: candidates in index order with their distance to the start
     for (int i = threadIdx.x; i < T; i += blockDim.x) {
         bool ok = i != start;
         for (int e = 0; e < n_exclude && ok; ++e) ok = (exclude[e] != (int64_t)i);
         inlist[i] = ok ? 1 : 0;
+        pos[i] = i;
         dist[i] = D[(long)i * ldd + start];
     }
     for (int i = threadIdx.x; i < k; i += blockDim.x) selected[i] = start;
@@ -129,6 +131,7 @@ furthest_sum_kernel(const double* __restrict__ D, long ldd, int T, int k, int st
             }
             dist[old] = qi;
             inlist[old] = 1;
+            pos[old] = T + step;              // appended at the end of the list
         }
         for (int e = threadIdx.x; e < ev; e += blockDim.x) H[(long)e * T + old] = INFINITY;
         __syncthreads();
@@ -168,7 +171,7 @@ static size_t fs_events(int k, int extra_steps)
 extern "C" size_t cdr_furthest_sum_workspace_bytes(int T, int k, int extra_steps)
 {
     const size_t Tp = ((size_t)T + 1) / 2 * 2;
-    return Tp * sizeof(double) + Tp * sizeof(int) + fs_events(k, extra_steps) * (size_t)T * sizeof(double);
+    return Tp * sizeof(double) + 2 * Tp * sizeof(int) + fs_events(k, extra_steps) * (size_t)T * sizeof(double);
 }
 
 extern "C" int cdr_furthest_sum(const double* D, long ldd, int T, int k, int start_index,
@@ -183,10 +186,11 @@ extern "C" int cdr_furthest_sum(const double* D, long ldd, int T, int k, int sta
     const size_t Tp = ((size_t)T + 1) / 2 * 2;
     double* dist = (double*)workspace;
     int* inlist = (int*)(dist + Tp);
-    double* H = (double*)(inlist + Tp);
+    int* pos = inlist + Tp;
+    double* H = (double*)(pos + Tp);
     furthest_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
         D, ldd, T, k, start_index, exclude, n_exclude, extra_steps < 0 ? 0 : extra_steps, selected,
-        dist, inlist, H);
+        dist, inlist, pos, H);
     CDR_RETURN_IF_LAUNCH_FAILED();
     return 0;
 }

@@ -68,7 +68,8 @@ template <int KPL>
 __global__ void __launch_bounds__(128)
 qp_batched_kernel(const double* __restrict__ A, const double* __restrict__ alpha,
                   const double* __restrict__ B, long sb_t, long sb_c, double* Z, int T, int k,
-                  cdr_spg_params p, int* n_iter_out, int* n_feval_out, const cdr_flags* flags)
+                  int spw, cdr_spg_params p, int* n_iter_out, int* n_feval_out,
+                  const cdr_flags* flags)
 {
     if (is_done(flags)) return;
     constexpr int KP = 8 * KPL;
@@ -90,8 +91,10 @@ qp_batched_kernel(const double* __restrict__ A, const double* __restrict__ alpha
     const int lane = threadIdx.x & 31;
     const int g = lane & 7;
     const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int t_raw = warp_global * 4 + (lane >> 3);
-    const bool valid = t_raw < T;
+    // spw samples per warp (1, 2 or 4): small batches use one sample per warp so that no
+    // sample waits in lock step for a slower neighbour (the kernel is latency bound)
+    const int t_raw = warp_global * spw + (lane >> 3);
+    const bool valid = ((lane >> 3) < spw) && (t_raw < T);
     const long t = valid ? t_raw : (T - 1);
 
     double arow[8];
@@ -141,7 +144,7 @@ qp_batched_kernel(const double* __restrict__ A, const double* __restrict__ alpha
     int n_feval = 1;
     int n_iter = 0;
     double alpha_s = 1.0;
-    bool active = true;      // group-uniform
+    bool active = valid;     // group-uniform
 
     for (int it = 0; it < p.max_iterations; ++it) {
         if (!__any_sync(CDR_FULL_MASK, active)) break;
@@ -190,17 +193,20 @@ qp_batched_kernel(const double* __restrict__ A, const double* __restrict__ alpha
         for (int i = 0; i < CDR_MAX_MEMORY; ++i)
             if (i < p.memory && !isnan(f_mem[i])) f_max = fmax(f_max, f_mem[i]);
 
-        // ---- line search (spg.py:349-372)
+        // ---- line search (spg.py:349-372).  Trial points are x_old + lam d; A x is linear
+        // in lam, so one extra mat-vec A d makes every backtracking trial a reduction only.
+        double Ad[KPL];
+        QpMatVec<KPL>::apply(As, arow, dk, Ad, g);
         double lam = 1.0;
-        double xn[KPL], Axn[KPL];
-#pragma unroll
-        for (int r = 0; r < KPL; ++r) xn[r] = xo[r] + dk[r];
-        QpMatVec<KPL>::apply(As, arow, xn, Axn, g);
+        double xn[KPL];
         double f_new;
         {
             double s = 0.0;
 #pragma unroll
-            for (int r = 0; r < KPL; ++r) s += xn[r] * (0.5 * Axn[r] + b[r]);
+            for (int r = 0; r < KPL; ++r) {
+                xn[r] = xo[r] + dk[r];
+                s += xn[r] * (0.5 * (Ax[r] + Ad[r]) + b[r]);
+            }
             f_new = group8_sum(s);
         }
         int fe = 1;
@@ -209,26 +215,32 @@ qp_batched_kernel(const double* __restrict__ A, const double* __restrict__ alpha
             double lam_t = lam;
             if (searching)
                 lam_t = spg_step_length(lam, delta, f_old, f_new, p.sigma_one, p.sigma_two);
-            double xt[KPL], Axt[KPL];
-#pragma unroll
-            for (int r = 0; r < KPL; ++r) xt[r] = xo[r] + lam_t * dk[r];
-            QpMatVec<KPL>::apply(As, arow, xt, Axt, g);
+            double xt[KPL];
             double s = 0.0;
 #pragma unroll
-            for (int r = 0; r < KPL; ++r) s += xt[r] * (0.5 * Axt[r] + b[r]);
+            for (int r = 0; r < KPL; ++r) {
+                xt[r] = xo[r] + lam_t * dk[r];
+                s += xt[r] * (0.5 * (Ax[r] + lam_t * Ad[r]) + b[r]);
+            }
             const double f_t = group8_sum(s);
             if (searching) {
                 lam = lam_t;
                 f_new = f_t;
                 fe += 1;
 #pragma unroll
-                for (int r = 0; r < KPL; ++r) {
-                    xn[r] = xt[r];
-                    Axn[r] = Axt[r];
-                }
+                for (int r = 0; r < KPL; ++r) xn[r] = xt[r];
                 if (fabs(lam) < p.lambda_min) searching = false;
                 else searching = f_new > f_max + p.gamma * lam * delta;
             }
+        }
+        // exact A x at the accepted point (gradient and f_old as in spg.py:374-386)
+        double Axn[KPL];
+        QpMatVec<KPL>::apply(As, arow, xn, Axn, g);
+        {
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < KPL; ++r) s += xn[r] * (0.5 * Axn[r] + b[r]);
+            f_new = group8_sum(s);
         }
 
         // ---- accept, spectral step length (spg.py:374-386)
@@ -289,16 +301,20 @@ static int launch_qp(const double* A, const double* alpha, const double* B, long
                      const cdr_flags* flags, cudaStream_t stream)
 {
     constexpr int KP = 8 * KPL;
-    // 4 samples per warp.  Few warps per CTA for small problems so that the
-    // samples spread over all SMs (the kernel is latency bound).
-    const int warps_needed = (T + 3) / 4;
+    // Samples per warp: one while every warp can still have (nearly) its own scheduler
+    // slot, up to four for large batches.  Few warps per CTA so the samples spread over
+    // all SMs (the kernel is latency bound).
+    int spw = 4;
+    if (T <= 148 * 4 * 6) spw = 1;
+    else if (T <= 148 * 4 * 16) spw = 2;
+    const int warps_needed = (T + spw - 1) / spw;
     int warps_per_block = 1;
-    if (warps_needed > 148 * 8) warps_per_block = 2;
-    if (warps_needed > 148 * 16) warps_per_block = 4;
+    if (warps_needed > 148 * 16) warps_per_block = 2;
+    if (warps_needed > 148 * 32) warps_per_block = 4;
     const int blocks = (warps_needed + warps_per_block - 1) / warps_per_block;
     const size_t smem = (KPL > 1) ? (size_t)KP * KP * sizeof(double) : 0;
     qp_batched_kernel<KPL><<<blocks, warps_per_block * 32, smem, stream>>>(
-        A, alpha, B, sb_t, sb_c, Z, T, k, p, n_iter, n_feval, flags);
+        A, alpha, B, sb_t, sb_c, Z, T, k, spw, p, n_iter, n_feval, flags);
     CDR_RETURN_IF_LAUNCH_FAILED();
     return 0;
 }

@@ -314,18 +314,46 @@ def gram(X, T, d):
     return K
 
 
+_TRACE_T0 = [None]
+
+
+def trace(msg):
+    """``CDR_TRACE_TIMING=1``: synchronise and print the wall time since the last call."""
+    if os.environ.get('CDR_TRACE_TIMING', '0') != '1':
+        return
+    import sys
+    import time
+    torch_mod().cuda.synchronize()
+    now = time.perf_counter()
+    if _TRACE_T0[0] is not None:
+        sys.stderr.write('[cdr trace] %-32s %8.2f ms\n' % (msg, (now - _TRACE_T0[0]) * 1e3))
+    _TRACE_T0[0] = now
+
+
 def graphs_disabled():
     """``CDR_NO_CUDA_GRAPH=1`` launches every iteration eagerly (debugging aid)."""
     return os.environ.get('CDR_NO_CUDA_GRAPH', '0') == '1'
 
 
 def capture_graph(fn):
-    """Capture the kernels ``fn`` enqueues on the current stream into a CUDA graph."""
+    """Capture the kernels ``fn`` enqueues on the current stream into a CUDA graph.
+
+    Uses ``capture_begin`` / ``capture_end`` on a side stream directly: the
+    ``torch.cuda.graph`` context manager also runs ``gc.collect()`` and
+    ``torch.cuda.empty_cache()``, which costs tens of milliseconds (cudaFree of every cached
+    block) inside what is otherwise a 2 ms operation.
+    """
     torch = torch_mod()
     graph = torch.cuda.CUDAGraph()
-    torch.cuda.synchronize()
-    with torch.cuda.graph(graph):
-        fn()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        graph.capture_begin()
+        try:
+            fn()
+        finally:
+            graph.capture_end()
+    torch.cuda.current_stream().wait_stream(side)
     return graph
 
 

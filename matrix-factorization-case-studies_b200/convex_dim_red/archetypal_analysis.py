@@ -284,7 +284,9 @@ class _AaEngine:
         if use_graph is None:
             use_graph = not be.graphs_disabled()
         use_graph = use_graph and self.graph_capturable() and not verbose
+        be.trace('aa: engine ready')
         self.initial_cost()
+        be.trace('aa: initial cost')
         max_it = self.state.max_iterations
         if verbose:
             print("*** {}: n_components = {:d} ***".format(label, self.k))
@@ -294,6 +296,7 @@ class _AaEngine:
         self.iteration()
         launched = 1
         st = self.state.read()
+        be.trace('aa: first iteration')
         if verbose:
             print('{:12d} | {: 12.6e} | {: 12.6e}'.format(st.n_iter, st.cost, st.cost - st.old_cost))
         chunk = 1
@@ -301,6 +304,7 @@ class _AaEngine:
         while not st.done and launched < max_it:
             if use_graph and graph is None:
                 graph = be.capture_graph(self.iteration)
+                be.trace('aa: graph capture')
             n = min(chunk, max_it - launched)
             for _ in range(n):
                 if graph is not None:
@@ -317,6 +321,7 @@ class _AaEngine:
         torch.cuda.synchronize()
         elapsed = time.perf_counter() - start
         st = self.state.read()
+        be.trace('aa: remaining iterations')
         if st.error_stage:
             raise RuntimeError('factorization cost increased after {} update'.format(
                 _STAGES[st.error_stage]))
@@ -558,6 +563,7 @@ def _update_kernel_aa_weights(weights, alpha, CK, CKCt, **solver_kwargs):
 def _iterate(data, weights, dictionary, alpha, mode, delta, update_weights,
              update_dictionary, update_scale_factors, tolerance, max_iterations, verbose,
              kwargs):
+    be.trace('aa: enter _iterate')
     eng = _engine(
         data, weights, dictionary, alpha, mode, delta=delta, tolerance=tolerance,
         max_iterations=max_iterations,
@@ -573,6 +579,7 @@ def _iterate(data, weights, dictionary, alpha, mode, delta, update_weights,
     new_weights = eng.weights() if update_weights else weights
     new_dictionary = eng.dictionary() if update_dictionary else dictionary
     new_alpha = eng.scale_factors() if (update_scale_factors and delta != 0) else alpha
+    be.trace('aa: results to host')
     return (new_weights, new_dictionary, new_alpha, eng.cost, eng.n_iter,
             eng.avg_time_per_iter, eng.cost_deltas)
 

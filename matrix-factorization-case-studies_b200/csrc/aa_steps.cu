@@ -341,16 +341,20 @@ __device__ __forceinline__ bool aa_cost_increased(double old_cost, double new_co
 }
 
 // cost from traces (archetypal_analysis.py:555-556, 623-652) + monotonicity / stopping tests
-__global__ void aa_cost_kernel(cdr_aa_buffers b, int stage, int end_of_iteration)
+__global__ void __launch_bounds__(32) aa_cost_kernel(cdr_aa_buffers b, int stage, int end_of_iteration)
 {
     cdr_loop_state* st = b.state;
-    if (st->done) return;
-    const int k = b.k;
+    if (*((volatile int*)&st->done)) return;
+    const int k = b.k, lane = threadIdx.x;
     double t1 = 0.0, t2 = 0.0;
-    for (int i = 0; i < k; ++i) t1 += b.alpha[i] * b.CKZ[i * k + i];
-    for (int i = 0; i < k; ++i)
-        for (int j = 0; j < k; ++j)
-            t2 += b.alpha[i] * b.alpha[j] * b.ZtZ[i * k + j] * b.CKCt[j * k + i];
+    for (int idx = lane; idx < k * k; idx += 32) {
+        const int i = idx / k, j = idx % k;
+        if (i == j) t1 += b.alpha[i] * b.CKZ[idx];
+        t2 += b.alpha[i] * b.alpha[j] * b.ZtZ[idx] * b.CKCt[j * k + i];
+    }
+    t1 = warp_sum(t1);
+    t2 = warp_sum(t2);
+    if (lane != 0) return;
     const double cost = 0.5 * (st->trace_data - 2.0 * t1 + t2) / (double)b.T;
     st->cost = cost;
     if (stage == 0) return;
@@ -495,7 +499,7 @@ extern "C" int cdr_aa_cost_check(const cdr_aa_buffers* b, int stage, int end_of_
                                  cdr_stream_t stream)
 {
     CDR_AA_CHECK(b);
-    aa_cost_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(*b, stage, end_of_iteration);
+    aa_cost_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(*b, stage, end_of_iteration);
     CDR_RETURN_IF_LAUNCH_FAILED();
     return 0;
 }

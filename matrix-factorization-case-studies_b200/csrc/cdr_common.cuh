@@ -143,4 +143,15 @@ __host__ __device__ __forceinline__ double spg_cauchy_step(double beta, double s
 
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
+// stream_tma.cu: bulk-copy pipelined variants; return CDR_TMA_NOT_APPLICABLE when the
+// shape should be handled by the direct-load kernels of stream_gemm.cu
+#define CDR_TMA_NOT_APPLICABLE (-100)
+int run_reduce_samples_tma(const double* Lp, long sLi, long sLt, const double* X, long ldx, int T,
+                           int d, int k, const double* E, double* out, long ldo,
+                           const cdr_flags* flags, cudaStream_t stream);
+int run_reduce_features_tma(const double* M, long ldm, const double* X, long ldx, int T, int d,
+                            int k, double* out, long ldo, void* workspace, size_t workspace_bytes,
+                            const cdr_flags* flags, cudaStream_t stream);
+size_t reduce_features_tma_workspace_bytes(int T, int d, int k);
+
 }  // namespace cdr

@@ -17,7 +17,8 @@ struct GramBatch {
     int nblk[CDR_GRAM_BATCH];
 };
 
-// partial[desc][blk][pair]
+// partial[desc][blk][pair].  256 threads = (pair slot, column sub-lane): with few pairs
+// (k = 8 -> 64) four sub-lanes share the columns of a tile, so the whole CTA works.
 __global__ void __launch_bounds__(256)
 small_gram_partial_kernel(GramBatch batch, double* __restrict__ part, const cdr_flags* flags)
 {
@@ -27,8 +28,12 @@ small_gram_partial_kernel(GramBatch batch, double* __restrict__ part, const cdr_
     if ((int)blockIdx.x >= nblk) return;
     __shared__ double As[CDR_MAX_COMPONENTS][kGramTile + 1];
     __shared__ double Bs[CDR_MAX_COMPONENTS][kGramTile + 1];
+    __shared__ double red[256];
 
     const int ka = ds.ka, kb = ds.kb, npairs = ka * kb;
+    const int nsub = (npairs <= 64) ? 4 : (npairs <= 128) ? 2 : 1;
+    const int slots = 256 / nsub;                  // pair slots per pass
+    const int slot = threadIdx.x % slots, sub = threadIdx.x / slots;
     int chunk = (ds.n + nblk - 1) / nblk;
     chunk = (chunk + kGramTile - 1) / kGramTile * kGramTile;
     const int n0 = blockIdx.x * chunk;
@@ -51,16 +56,14 @@ small_gram_partial_kernel(GramBatch batch, double* __restrict__ part, const cdr_
         __syncthreads();
 #pragma unroll
         for (int s = 0; s < kGramMaxPairs / 256; ++s) {
-            const int p = threadIdx.x + s * 256;
-            if (p < npairs) {
+            const int p = slot + s * slots;
+            if (p < npairs && (s == 0 || nsub == 1)) {
                 const int i = p / kb, j = p % kb;
                 double a = acc[s];
                 if (ds.mode == 0) {
-#pragma unroll 8
-                    for (int cix = 0; cix < kGramTile; ++cix) a = fma(As[i][cix], Bs[j][cix], a);
+                    for (int cix = sub; cix < kGramTile; cix += nsub) a = fma(As[i][cix], Bs[j][cix], a);
                 } else {
-#pragma unroll 8
-                    for (int cix = 0; cix < kGramTile; ++cix) {
+                    for (int cix = sub; cix < kGramTile; cix += nsub) {
                         const double df = As[i][cix] - Bs[j][cix];
                         a = fma(df, df, a);
                     }
@@ -71,13 +74,24 @@ small_gram_partial_kernel(GramBatch batch, double* __restrict__ part, const cdr_
         __syncthreads();
     }
     double* dst = part + ((long)blockIdx.y * kGramMaxBlocks + blockIdx.x) * kGramMaxPairs;
+    if (nsub == 1) {
 #pragma unroll
-    for (int s = 0; s < kGramMaxPairs / 256; ++s) {
-        const int p = threadIdx.x + s * 256;
-        if (p < npairs) dst[p] = acc[s];
+        for (int s = 0; s < kGramMaxPairs / 256; ++s) {
+            const int p = threadIdx.x + s * 256;
+            if (p < npairs) dst[p] = acc[s];
+        }
+    } else {
+        red[threadIdx.x] = acc[0];
+        __syncthreads();
+        if (sub == 0 && slot < npairs) {
+            double v = 0.0;
+            for (int q = 0; q < nsub; ++q) v += red[q * slots + slot];     // fixed order
+            dst[slot] = v;
+        }
     }
 }
 
+// out = scale * sum over blocks, fixed order.  256 threads = (pair, group of blocks).
 __global__ void __launch_bounds__(256)
 small_gram_final_kernel(GramBatch batch, const double* __restrict__ part, const cdr_flags* flags)
 {
@@ -85,11 +99,28 @@ small_gram_final_kernel(GramBatch batch, const double* __restrict__ part, const 
     const cdr_small_gram_desc& ds = batch.d[blockIdx.x];
     const int nblk = batch.nblk[blockIdx.x];
     const int npairs = ds.ka * ds.kb;
-    for (int p = threadIdx.x; p < npairs; p += 256) {
-        const double* src = part + ((long)blockIdx.x * kGramMaxBlocks) * kGramMaxPairs + p;
+    __shared__ double red[256];
+    const double* base = part + ((long)blockIdx.x * kGramMaxBlocks) * kGramMaxPairs;
+    if (npairs <= 64) {
+        const int groups = 256 / 64;
+        const int p = threadIdx.x % 64, g = threadIdx.x / 64;
+        const int per = (nblk + groups - 1) / groups;
         double s = 0.0;
-        for (int b = 0; b < nblk; ++b) s += src[(long)b * kGramMaxPairs];   // fixed order
-        ds.out[p] = ds.scale * s;
+        if (p < npairs)
+            for (int b = g * per; b < min(nblk, (g + 1) * per); ++b) s += base[(long)b * kGramMaxPairs + p];
+        red[threadIdx.x] = s;
+        __syncthreads();
+        if (g == 0 && p < npairs) {
+            double v = 0.0;
+            for (int q = 0; q < groups; ++q) v += red[q * 64 + p];
+            ds.out[p] = ds.scale * v;
+        }
+    } else {
+        for (int p = threadIdx.x; p < npairs; p += 256) {
+            double s = 0.0;
+            for (int b = 0; b < nblk; ++b) s += base[(long)b * kGramMaxPairs + p];
+            ds.out[p] = ds.scale * s;
+        }
     }
 }
 
@@ -260,26 +291,31 @@ __global__ void loop_begin_kernel(cdr_loop_state* st)
     st->old_cost = st->cost;
 }
 
-__global__ void gpnh_cost_kernel(cdr_loop_state* st, double* cost_deltas,
-                                 const double* __restrict__ XWtZ, const double* __restrict__ ZtZ,
-                                 const double* __restrict__ WtW, const double* __restrict__ reg_pairs,
-                                 int k, int n_samples, int n_features, double lambda_W, int stage,
-                                 int end_of_iteration)
+__global__ void __launch_bounds__(32)
+gpnh_cost_kernel(cdr_loop_state* st, double* cost_deltas, const double* __restrict__ XWtZ,
+                 const double* __restrict__ ZtZ, const double* __restrict__ WtW,
+                 const double* __restrict__ reg_pairs, int k, int n_samples, int n_features,
+                 double lambda_W, int stage, int end_of_iteration)
 {
-    if (st->done) return;
-    double tr1 = 0.0, tr2 = 0.0;
-    for (int i = 0; i < k; ++i) tr1 += XWtZ[i * k + i];
-    for (int i = 0; i < k; ++i)
-        for (int j = 0; j < k; ++j) tr2 += ZtZ[i * k + j] * WtW[j * k + i];
+    if (*((volatile int*)&st->done)) return;
+    const int lane = threadIdx.x;
+    double tr1 = 0.0, tr2 = 0.0, phi = 0.0;
+    for (int idx = lane; idx < k * k; idx += 32) {
+        const int i = idx / k, j = idx % k;
+        if (i == j) tr1 += XWtZ[idx];
+        tr2 += ZtZ[idx] * WtW[j * k + i];
+        if (reg_pairs != nullptr && j > i) phi += reg_pairs[idx];
+    }
+    tr1 = warp_sum(tr1);
+    tr2 = warp_sum(tr2);
+    phi = warp_sum(phi);
+    if (lane != 0) return;
     if (reg_pairs != nullptr) {
         // gpnh_convex_coding.py:179-196
-        double phi = 0.0;
-        if (lambda_W != 0.0 && k > 1) {
-            for (int i = 0; i < k; ++i)
-                for (int j = i + 1; j < k; ++j) phi += reg_pairs[i * k + j];
-            phi *= 2.0 / ((double)k * (double)n_features * ((double)k - 1.0));
-        }
-        st->penalty = (lambda_W != 0.0) ? lambda_W * phi : 0.0;
+        double pen = 0.0;
+        if (lambda_W != 0.0 && k > 1)
+            pen = lambda_W * phi * 2.0 / ((double)k * (double)n_features * ((double)k - 1.0));
+        st->penalty = pen;
     }
     const double cost = 0.5 * (st->trace_data - 2.0 * tr1 + tr2) / (double)n_samples + st->penalty;
     finish_sub_step(st, cost_deltas, cost, stage, end_of_iteration);
@@ -307,7 +343,7 @@ extern "C" int cdr_small_gram(const cdr_small_gram_desc* descs, int count, void*
         CDR_CHECK_ARG(descs[i].ka >= 1 && descs[i].kb >= 1 && descs[i].n >= 0);
         if (descs[i].ka > CDR_MAX_COMPONENTS || descs[i].kb > CDR_MAX_COMPONENTS)
             return CDR_ERR_UNSUPPORTED;
-        int nb = (descs[i].n + 255) / 256;
+        int nb = (descs[i].n + 127) / 128;
         if (nb < 1) nb = 1;
         if (nb > kGramMaxBlocks) nb = kGramMaxBlocks;
         batch.nblk[i] = nb;
@@ -346,7 +382,9 @@ extern "C" int cdr_gpnh_solve_matrix(const double* ZtZ, int k, int n_samples, in
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    gpnh_solve_matrix_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(
+    // k/2 * k work items per Jacobi phase: one warp is enough (and cheapest to synchronise)
+    // up to k = 16
+    gpnh_solve_matrix_kernel<<<1, k <= 16 ? 32 : 256, smem, (cudaStream_t)stream>>>(
         ZtZ, k, 1.0 / (double)n_samples, lambda_W, pref, P, flags);
     CDR_RETURN_IF_LAUNCH_FAILED();
     return 0;
@@ -365,7 +403,7 @@ extern "C" int cdr_sym_pinv(const double* S, int k, double* P, const cdr_flags* 
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    gpnh_solve_matrix_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(S, k, 1.0, 0.0, 0.0, P, flags);
+    gpnh_solve_matrix_kernel<<<1, k <= 16 ? 32 : 256, smem, (cudaStream_t)stream>>>(S, k, 1.0, 0.0, 0.0, P, flags);
     CDR_RETURN_IF_LAUNCH_FAILED();
     return 0;
 }
@@ -384,7 +422,7 @@ extern "C" int cdr_gpnh_cost_check(cdr_loop_state* state, double* cost_deltas, c
                                    int stage, int end_of_iteration, cdr_stream_t stream)
 {
     CDR_CHECK_ARG(state != nullptr && k >= 1);
-    gpnh_cost_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, cost_deltas, XWtZ, ZtZ, WtW,
+    gpnh_cost_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(state, cost_deltas, XWtZ, ZtZ, WtW,
                                                         reg_pairs, k, n_samples, n_features,
                                                         lambda_W, stage, end_of_iteration);
     CDR_RETURN_IF_LAUNCH_FAILED();

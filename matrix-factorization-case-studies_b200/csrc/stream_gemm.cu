@@ -445,6 +445,10 @@ extern "C" int cdr_reduce_samples(const double* Lp, long sLi, long sLt, const do
     const int dpad = (d + 31) / 32 * 32;
     CDR_CHECK_ARG(ldx >= dpad && ldo >= dpad && ldx % 2 == 0 && ldo % 2 == 0);
     cudaStream_t s = (cudaStream_t)stream;
+    {
+        const int rc = run_reduce_samples_tma(Lp, sLi, sLt, X, ldx, T, d, k, E, out, ldo, flags, s);
+        if (rc != CDR_TMA_NOT_APPLICABLE) return rc;
+    }
 #define CALL(KT) return run_reduce_samples<KT>(Lp, sLi, sLt, X, ldx, T, d, k, E, out, ldo, workspace, workspace_bytes, flags, s)
     CDR_DISPATCH_KT(k, CALL);
 #undef CALL
@@ -457,7 +461,9 @@ extern "C" size_t cdr_reduce_features_workspace_bytes(int T, int d, int k)
     int nchunk, chunk;
     features_split(T, dpad, &nchunk, &chunk);
     const int kp = (k <= 8) ? 8 : (k <= 16) ? 16 : (k <= 24) ? 24 : (k <= 32) ? 32 : (k <= 48) ? 48 : 64;
-    return (size_t)nchunk * T * kp * sizeof(double);
+    const size_t direct = (size_t)nchunk * T * kp * sizeof(double);
+    const size_t piped = reduce_features_tma_workspace_bytes(T, d, k);
+    return direct > piped ? direct : piped;
 }
 
 extern "C" int cdr_reduce_features(const double* M, long ldm, const double* X, long ldx, int T,
@@ -470,6 +476,11 @@ extern "C" int cdr_reduce_features(const double* M, long ldm, const double* X, l
     const int dpad = (d + 31) / 32 * 32;
     CDR_CHECK_ARG(ldx >= dpad && ldm >= dpad && ldo >= T && ldx % 2 == 0 && ldm % 2 == 0);
     cudaStream_t s = (cudaStream_t)stream;
+    {
+        const int rc = run_reduce_features_tma(M, ldm, X, ldx, T, d, k, out, ldo, workspace,
+                                               workspace_bytes, flags, s);
+        if (rc != CDR_TMA_NOT_APPLICABLE) return rc;
+    }
 #define CALL(KT) return run_reduce_features<KT>(M, ldm, X, ldx, T, d, k, out, ldo, workspace, workspace_bytes, flags, s)
     CDR_DISPATCH_KT(k, CALL);
 #undef CALL

@@ -1,0 +1,560 @@
+// TMA-pipelined versions of the two streaming contractions (see stream_gemm.cu for
+// the operation definitions and the fragment trick, stream_tma.cuh for the
+// pipeline).  These are the production path at HadISST-like shapes; the
+// direct-load kernels of stream_gemm.cu remain for shapes these do not cover
+// (few features, k > 16 for the feature reduction).
+//
+//   reduce over samples  : a CTA owns a strip of TC ~ d/148 features and streams all
+//                          T rows of it in 8-row stages; every consumer warp keeps
+//                          the accumulators of its 16-feature units for the whole
+//                          strip, so there are no partial sums, no workspace and no
+//                          second kernel -- the k x k epilogue (E) is applied from
+//                          shared memory before the single coalesced store.
+//   reduce over features : the same strip-owned tile stream; the strip of M lives in
+//                          registers as DMMA B fragments, the per-stage results of
+//                          the four feature quarters are combined through shared
+//                          memory and written as per-strip partials (a few % of the
+//                          bytes of X), summed in fixed order by a finalize kernel.
+#include "stream_tma.cuh"
+
+namespace cdr {
+
+using namespace tma;
+
+// ======================================================================
+// reduce over samples (strip owned)
+// ======================================================================
+// rows per stage (four DMMA k-steps).  Measured with profiles/probes/tma_probe.cu: the
+// bulk-copy ring needs >= ~32 KB per stage to reach the HBM peak (8 rows x 2.4 KB stalls at
+// 4.6 TB/s whatever the ring depth, 16 rows reach 6.5 TB/s).
+constexpr int kSampTR = 16;
+constexpr int kSampKS = kSampTR / 4;
+
+template <int KT, int MAXU, bool FUSE_E>
+__global__ void __launch_bounds__(kThreads, 1)
+reduce_samples_tma_kernel(const double* __restrict__ Lp, long sLi, long sLt,
+                          const double* __restrict__ X, long ldx, int T, int dpad, int k, int TC,
+                          int nstrips, int stages, const double* __restrict__ E,
+                          double* __restrict__ out, long ldo, const cdr_flags* flags)
+{
+    if (is_done(flags)) return;
+    constexpr int KP = 8 * KT;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+    double* Es = reinterpret_cast<double*>(smem_raw + 128);
+    double* epi = Es + (FUSE_E ? KP * KP : 0);
+    double* tiles = epi + (FUSE_E ? kConsumerWarps * KP * 20 : 0);
+    const int RS = TC + 4;                       // row stride (doubles): == 4 mod 16, conflict free
+    const long stage_doubles = (long)kSampTR * RS;
+
+    Pipeline pipe;
+    pipe.init(bars, stages);
+    if (FUSE_E) {
+        for (int idx = threadIdx.x; idx < KP * KP; idx += blockDim.x) {
+            const int j = idx / KP, i = idx % KP;
+            Es[idx] = (j < k && i < k) ? E[j * k + i] : 0.0;
+        }
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntiles = (T + kSampTR - 1) / kSampTR;
+
+    if (warp == kConsumerWarps) {
+        // ------------------------------ producer warp: lane 0 owns the barriers, every
+        // lane issues the bulk copy of one row (a single thread issuing all copies of a
+        // stage is limited by the per-instruction issue latency, not by bytes)
+        int it = 0;
+        for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+            const int c0 = strip * TC;
+            const int w = min(TC, dpad - c0);
+            for (int rt = 0; rt < ntiles; ++rt, ++it) {
+                const int s = it % stages;
+                const uint32_t ph = (uint32_t)(it / stages) & 1u;
+                const int rows = min(kSampTR, T - rt * kSampTR);
+                if (lane == 0) {
+                    mbar_wait(&pipe.empty[s], ph ^ 1u);
+                    mbar_arrive_expect_tx(&pipe.full[s], (uint32_t)(rows * w * 8));
+                }
+                __syncwarp();
+                if (lane < rows) {
+                    double* dst = tiles + s * stage_doubles + (long)lane * RS;
+                    const double* src = X + (long)(rt * kSampTR + lane) * ldx + c0;
+                    bulk_g2s(dst, src, (uint32_t)(w * 8), &pipe.full[s]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------- consumers
+    const int lr = lane & 3, lc = lane >> 2;
+    int it = 0;
+    for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+        const int c0 = strip * TC;
+        const int w = min(TC, dpad - c0);
+        const int nunits = w / 16;
+
+        double acc[MAXU][KT][2][2];
+#pragma unroll
+        for (int u = 0; u < MAXU; ++u)
+#pragma unroll
+            for (int mt = 0; mt < KT; ++mt)
+                acc[u][mt][0][0] = acc[u][mt][0][1] = acc[u][mt][1][0] = acc[u][mt][1][1] = 0.0;
+
+        for (int rt = 0; rt < ntiles; ++rt, ++it) {
+            const int s = it % stages;
+            const uint32_t ph = (uint32_t)(it / stages) & 1u;
+            const int t0 = rt * kSampTR;
+            // left-operand fragments of the stage's k-steps, fetched before the wait
+            double a[kSampKS][KT];
+            bool rowok[kSampKS];
+#pragma unroll
+            for (int ks = 0; ks < kSampKS; ++ks) {
+                const int tt = t0 + 4 * ks + lr;
+                rowok[ks] = tt < T;
+#pragma unroll
+                for (int mt = 0; mt < KT; ++mt) {
+                    const int i = mt * 8 + lc;
+                    a[ks][mt] = (rowok[ks] && i < k) ? Lp[(long)i * sLi + (long)tt * sLt] : 0.0;
+                }
+            }
+            mbar_wait(&pipe.full[s], ph);
+            const double* tl = tiles + s * stage_doubles;
+#pragma unroll
+            for (int ks = 0; ks < kSampKS; ++ks) {
+                const double* rowp = tl + (long)(4 * ks + lr) * RS + 2 * lc;
+#pragma unroll
+                for (int u = 0; u < MAXU; ++u) {
+                    const int unit = warp + kConsumerWarps * u;
+                    if (unit < nunits) {
+                        double2 xv = make_double2(0.0, 0.0);
+                        if (rowok[ks]) xv = *reinterpret_cast<const double2*>(rowp + unit * 16);
+#pragma unroll
+                        for (int mt = 0; mt < KT; ++mt) {
+                            dmma884(acc[u][mt][0][0], acc[u][mt][0][1], a[ks][mt], xv.x);
+                            dmma884(acc[u][mt][1][0], acc[u][mt][1][1], a[ks][mt], xv.y);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&pipe.empty[s]);
+        }
+
+        // ------------------------------ epilogue of the strip
+        // lane holds, for row i = mt*8 + lc, features unit*16 + 4*lr + {0,1,2,3}
+        //   = (acc[..][0][0], acc[..][1][0], acc[..][0][1], acc[..][1][1])
+#pragma unroll
+        for (int u = 0; u < MAXU; ++u) {
+            const int unit = warp + kConsumerWarps * u;
+            if (unit >= nunits) continue;
+            const int fbase = c0 + unit * 16;
+            if (!FUSE_E) {
+#pragma unroll
+                for (int mt = 0; mt < KT; ++mt) {
+                    const int i = mt * 8 + lc;
+                    if (i < k) {
+                        double* p = out + (long)i * ldo + fbase + 4 * lr;
+                        *reinterpret_cast<double2*>(p) =
+                            make_double2(acc[u][mt][0][0], acc[u][mt][1][0]);
+                        *reinterpret_cast<double2*>(p + 2) =
+                            make_double2(acc[u][mt][0][1], acc[u][mt][1][1]);
+                    }
+                }
+            } else {
+                double* eb = epi + warp * (KP * 20);
+#pragma unroll
+                for (int mt = 0; mt < KT; ++mt) {
+                    double* p = eb + (mt * 8 + lc) * 20 + 4 * lr;
+                    p[0] = acc[u][mt][0][0];
+                    p[1] = acc[u][mt][1][0];
+                    p[2] = acc[u][mt][0][1];
+                    p[3] = acc[u][mt][1][1];
+                }
+                __syncwarp();
+                const int f = lane & 15, jh = lane >> 4;
+                double col[KP];
+#pragma unroll
+                for (int i = 0; i < KP; ++i) col[i] = eb[i * 20 + f];
+                for (int j = jh; j < k; j += 2) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int i = 0; i < KP; ++i) sacc = fma(Es[j * KP + i], col[i], sacc);
+                    out[(long)j * ldo + fbase + f] = sacc;
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+// ======================================================================
+// reduce over features (strip owned)
+// ======================================================================
+// Same tile stream as the reduce over samples (the access pattern that reaches the HBM
+// peak in profiles/probes/tma_probe.cu): a CTA owns a strip of TC features and walks
+// down all T rows in 16-row stages.  The strip of M (k x TC) is held in registers as DMMA
+// B fragments for the whole strip.  Warp w handles m-tile (w & 1) of the stage and the
+// feature quarter (w >> 1); the four quarter results of a stage are combined through a
+// double-buffered shared-memory exchange (one 256-thread named barrier per stage) and
+// written as the strip's partial out[strip][t][j]; the strips are summed in fixed order by
+// reduce_features_strip_finalize_kernel.
+constexpr int kFsTR = 16;
+
+__device__ __forceinline__ void consumer_barrier()
+{
+    asm volatile("bar.sync 1, %0;\n" ::"n"(kConsumerWarps * 32) : "memory");
+}
+
+template <int KT, int MAXUQ>
+__global__ void __launch_bounds__(kThreads, 1)
+reduce_features_strip_kernel(const double* __restrict__ M, long ldm, const double* __restrict__ X,
+                             long ldx, int T, int dpad, int k, int TC, int nstrips, int stages,
+                             double* __restrict__ part, const cdr_flags* flags)
+{
+    if (is_done(flags)) return;
+    constexpr int KP = 8 * KT;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+    double* red = reinterpret_cast<double*>(smem_raw + 128);      // [2][4][2][8][KP]
+    double* tiles = red + 2 * 4 * 2 * 8 * KP;
+    const int RS = TC + 8;                       // == 8 mod 16: conflict-free row fragments
+    const long stage_doubles = (long)kFsTR * RS;
+
+    Pipeline pipe;
+    pipe.init(bars, stages);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntiles = (T + kFsTR - 1) / kFsTR;
+
+    if (warp == kConsumerWarps) {
+        int it = 0;
+        for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+            const int c0 = strip * TC;
+            const int w = min(TC, dpad - c0);
+            for (int rt = 0; rt < ntiles; ++rt, ++it) {
+                const int s = it % stages;
+                const uint32_t ph = (uint32_t)(it / stages) & 1u;
+                const int rows = min(kFsTR, T - rt * kFsTR);
+                if (lane == 0) {
+                    mbar_wait(&pipe.empty[s], ph ^ 1u);
+                    mbar_arrive_expect_tx(&pipe.full[s], (uint32_t)(rows * w * 8));
+                }
+                __syncwarp();
+                if (lane < rows)
+                    bulk_g2s(tiles + s * stage_doubles + (long)lane * RS,
+                             X + (long)(rt * kFsTR + lane) * ldx + c0, (uint32_t)(w * 8),
+                             &pipe.full[s]);
+            }
+        }
+        return;
+    }
+
+    const int lr = lane & 3, lc = lane >> 2;
+    const int mt = warp & 1, fq = warp >> 1;
+    int it = 0;
+    for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+        const int c0 = strip * TC;
+        const int w = min(TC, dpad - c0);
+        const int nunits = w / 16;
+
+        // B fragments of the strip of M: M[j = nt*8 + lc][unit*16 + 8p + 2*lr + {0,1}]
+        double2 breg[MAXUQ][2][KT];
+#pragma unroll
+        for (int uq = 0; uq < MAXUQ; ++uq) {
+            const int unit = fq + 4 * uq;
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+#pragma unroll
+                for (int nt = 0; nt < KT; ++nt) {
+                    const int j = nt * 8 + lc;
+                    double2 v = make_double2(0.0, 0.0);
+                    if (unit < nunits && j < k)
+                        v = *reinterpret_cast<const double2*>(M + (long)j * ldm + c0 + unit * 16 +
+                                                              8 * p + 2 * lr);
+                    breg[uq][p][nt] = v;
+                }
+        }
+
+        for (int rt = 0; rt < ntiles; ++rt, ++it) {
+            const int s = it % stages;
+            const uint32_t ph = (uint32_t)(it / stages) & 1u;
+            const int t = rt * kFsTR + 8 * mt + lc;
+            const bool rowok = t < T;
+            double acc[KT][2];
+#pragma unroll
+            for (int nt = 0; nt < KT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+
+            mbar_wait(&pipe.full[s], ph);
+            const double* rowp = tiles + s * stage_doubles + (long)(8 * mt + lc) * RS + 2 * lr;
+#pragma unroll
+            for (int uq = 0; uq < MAXUQ; ++uq) {
+                const int unit = fq + 4 * uq;
+                if (unit < nunits) {
+#pragma unroll
+                    for (int p = 0; p < 2; ++p) {
+                        double2 xa = make_double2(0.0, 0.0);
+                        if (rowok) xa = *reinterpret_cast<const double2*>(rowp + unit * 16 + 8 * p);
+#pragma unroll
+                        for (int nt = 0; nt < KT; ++nt) {
+                            dmma884(acc[nt][0], acc[nt][1], xa.x, breg[uq][p][nt].x);
+                            dmma884(acc[nt][0], acc[nt][1], xa.y, breg[uq][p][nt].y);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&pipe.empty[s]);
+
+            // combine the four feature quarters of this stage (fixed order)
+            const int buf = it & 1;
+            double* mine = red + (((buf * 4 + fq) * 2 + mt) * 8 + lc) * KP + 2 * lr;
+#pragma unroll
+            for (int nt = 0; nt < KT; ++nt)
+                *reinterpret_cast<double2*>(mine + nt * 8) = make_double2(acc[nt][0], acc[nt][1]);
+            consumer_barrier();
+            if (fq == 0 && rowok) {
+                double* dst = part + ((long)strip * T + t) * KP + 2 * lr;
+#pragma unroll
+                for (int nt = 0; nt < KT; ++nt) {
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const double2 v = *reinterpret_cast<const double2*>(
+                            red + (((buf * 4 + q) * 2 + mt) * 8 + lc) * KP + 2 * lr + nt * 8);
+                        s0 += v.x;
+                        s1 += v.y;
+                    }
+                    *reinterpret_cast<double2*>(dst + nt * 8) = make_double2(s0, s1);
+                }
+            }
+        }
+    }
+}
+
+// out[j][t] = sum_strip part[strip][t][j].  A CTA handles 32 (t, component pair) items;
+// its 8 warps sum disjoint groups of strips which are then combined in fixed order.
+template <int KT>
+__global__ void __launch_bounds__(256)
+reduce_features_strip_finalize_kernel(const double* __restrict__ part, int T, int nstrips, int k,
+                                      double* __restrict__ out, long ldo, const cdr_flags* flags)
+{
+    if (is_done(flags)) return;
+    constexpr int KP = 8 * KT;
+    constexpr int PAIRS = KP / 2;
+    __shared__ double2 red[8][32];
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const long item = (long)blockIdx.x * 32 + lane;
+    const long nitems = (long)T * PAIRS;
+    const long stride = nitems;                                   // double2 per strip
+    const int per = (nstrips + 7) / 8;
+    double s0 = 0.0, s1 = 0.0;
+    if (item < nitems) {
+        const double2* src = reinterpret_cast<const double2*>(part) + item;
+        const int hi = min(nstrips, (g + 1) * per);
+        int sidx = g * per;
+        for (; sidx + 2 <= hi; sidx += 2) {
+            const double2 v0 = src[(long)sidx * stride];
+            const double2 v1 = src[(long)(sidx + 1) * stride];
+            s0 += v0.x; s1 += v0.y;
+            s0 += v1.x; s1 += v1.y;
+        }
+        for (; sidx < hi; ++sidx) {
+            const double2 v = src[(long)sidx * stride];
+            s0 += v.x;
+            s1 += v.y;
+        }
+    }
+    red[g][lane] = make_double2(s0, s1);
+    __syncthreads();
+    if (g == 0 && item < nitems) {
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            a0 += red[q][lane].x;
+            a1 += red[q][lane].y;
+        }
+        const int t = (int)(item / PAIRS), j = 2 * (int)(item % PAIRS);
+        if (j < k) out[(long)j * ldo + t] = a0;
+        if (j + 1 < k) out[(long)(j + 1) * ldo + t] = a1;
+    }
+}
+
+// ---------------------------------------------------------------------- host side
+static int sm_count()
+{
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// CDR_DISABLE_TMA=1 forces the direct-load kernels (A/B testing of the two paths)
+static bool tma_disabled()
+{
+    const char* e = getenv("CDR_DISABLE_TMA");
+    return e != nullptr && e[0] == '1';
+}
+
+constexpr size_t kSmemBudget = 220 * 1024;
+
+template <auto Kern>
+static int ensure_smem(size_t smem)
+{
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = smem;
+    }
+    return 0;
+}
+
+// returns CDR_TMA_NOT_APPLICABLE when the shape should use the direct-load kernels
+template <int KT, int MAXU, bool FUSE_E>
+static int launch_samples_tma(const double* Lp, long sLi, long sLt, const double* X, long ldx, int T,
+                              int dpad, int k, int TC, int nstrips, const double* E, double* out,
+                              long ldo, const cdr_flags* flags, cudaStream_t stream)
+{
+    constexpr int KP = 8 * KT;
+    const size_t fixed = 128 + (FUSE_E ? ((size_t)KP * KP + (size_t)kConsumerWarps * KP * 20) * 8 : 0);
+    const size_t stage = (size_t)kSampTR * (TC + 4) * 8;
+    int stages = (int)((kSmemBudget - fixed) / stage);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) return CDR_TMA_NOT_APPLICABLE;
+    const size_t smem = fixed + stages * stage;
+    int rc = ensure_smem<reduce_samples_tma_kernel<KT, MAXU, FUSE_E>>(smem);
+    if (rc) return rc;
+    const int grid = nstrips < sm_count() ? nstrips : sm_count();
+    reduce_samples_tma_kernel<KT, MAXU, FUSE_E><<<grid, kThreads, smem, stream>>>(
+        Lp, sLi, sLt, X, ldx, T, dpad, k, TC, nstrips, stages, E, out, ldo, flags);
+    CDR_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+int run_reduce_samples_tma(const double* Lp, long sLi, long sLt, const double* X, long ldx, int T,
+                           int d, int k, const double* E, double* out, long ldo,
+                           const cdr_flags* flags, cudaStream_t stream)
+{
+    if (tma_disabled()) return CDR_TMA_NOT_APPLICABLE;
+    if (k > 32) return CDR_TMA_NOT_APPLICABLE;
+    if ((ldx % 2) != 0 || (((uintptr_t)X) & 15) != 0) return CDR_TMA_NOT_APPLICABLE;
+    const int dpad = (d + 31) / 32 * 32;
+    const int nsm = sm_count();
+    // strip width: a multiple of 16 features, as close to dpad / (m * #SM) as the unit allows
+    const int tc_max = (k <= 16) ? 512 : 256;
+    int waves = (dpad + nsm * tc_max - 1) / (nsm * tc_max);
+    if (waves < 1) waves = 1;
+    int TC = (dpad + nsm * waves - 1) / (nsm * waves);
+    TC = (TC + 15) / 16 * 16;
+    if (TC > tc_max) TC = tc_max;
+    const int nstrips = (dpad + TC - 1) / TC;
+    // few or narrow strips (Gram-space "X" = K, PCA-reduced data): split-T direct kernel
+    if (nstrips < nsm / 2 || TC < 64 || T < 64) return CDR_TMA_NOT_APPLICABLE;
+    const int kt = (k + 7) / 8;
+#define CDR_S(KT, MAXU)                                                                          \
+    do {                                                                                         \
+        if (E != nullptr && KT <= 2)                                                             \
+            return launch_samples_tma<KT, MAXU, true>(Lp, sLi, sLt, X, ldx, T, dpad, k, TC,      \
+                                                      nstrips, E, out, ldo, flags, stream);      \
+        if (E != nullptr) return CDR_TMA_NOT_APPLICABLE;                                         \
+        return launch_samples_tma<KT, MAXU, false>(Lp, sLi, sLt, X, ldx, T, dpad, k, TC, nstrips, \
+                                                   nullptr, out, ldo, flags, stream);            \
+    } while (0)
+    if (kt == 1) CDR_S(1, 4);
+    if (kt == 2) CDR_S(2, 4);
+    if (kt == 3) CDR_S(3, 2);
+    CDR_S(4, 2);
+#undef CDR_S
+}
+
+// strip width shared by the two strip-owned kernels: a multiple of 16 features, as close to
+// dpad / (waves * #SM) as the unit allows
+static void strip_geometry(int dpad, int tc_max, int* TC, int* nstrips)
+{
+    const int nsm = sm_count();
+    int waves = (dpad + nsm * tc_max - 1) / (nsm * tc_max);
+    if (waves < 1) waves = 1;
+    int tc = (dpad + nsm * waves - 1) / (nsm * waves);
+    tc = (tc + 15) / 16 * 16;
+    if (tc > tc_max) tc = tc_max;
+    *TC = tc;
+    *nstrips = (dpad + tc - 1) / tc;
+}
+
+constexpr int kFsTcMax = 384;
+
+static bool features_strip_ok(const double* M, long ldm, const double* X, long ldx, int T, int d,
+                              int k, int* TC, int* nstrips)
+{
+    if (tma_disabled() || k > 16) return false;
+    if ((ldx % 2) != 0 || (ldm % 2) != 0) return false;
+    if ((((uintptr_t)X) & 15) != 0 || (((uintptr_t)M) & 15) != 0) return false;
+    const int dpad = (d + 31) / 32 * 32;
+    strip_geometry(dpad, kFsTcMax, TC, nstrips);
+    if (*nstrips < sm_count() / 2 || *TC < 64 || T < 64) return false;
+    // the per-strip partials must stay a small fraction of the bytes of X
+    const int kp = (k + 7) / 8 * 8;
+    return (long)(*nstrips) * kp * 10 <= (long)dpad;
+}
+
+template <int KT>
+static int launch_features_strip(const double* M, long ldm, const double* X, long ldx, int T,
+                                 int dpad, int k, int TC, int nstrips, double* out, long ldo,
+                                 void* workspace, size_t workspace_bytes, const cdr_flags* flags,
+                                 cudaStream_t stream)
+{
+    constexpr int KP = 8 * KT;
+    constexpr int MAXUQ = kFsTcMax / 16 / 4;
+    const size_t need = (size_t)nstrips * T * KP * sizeof(double);
+    if (workspace == nullptr || workspace_bytes < need) return CDR_ERR_WORKSPACE;
+    const size_t fixed = 128 + (size_t)2 * 4 * 2 * 8 * KP * 8;
+    const size_t stage = (size_t)kFsTR * (TC + 8) * 8;
+    int stages = (int)((kSmemBudget - fixed) / stage);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) return CDR_TMA_NOT_APPLICABLE;
+    const size_t smem = fixed + stages * stage;
+    int rc = ensure_smem<reduce_features_strip_kernel<KT, MAXUQ>>(smem);
+    if (rc) return rc;
+    const int grid = nstrips < sm_count() ? nstrips : sm_count();
+    reduce_features_strip_kernel<KT, MAXUQ><<<grid, kThreads, smem, stream>>>(
+        M, ldm, X, ldx, T, dpad, k, TC, nstrips, stages, (double*)workspace, flags);
+    CDR_RETURN_IF_LAUNCH_FAILED();
+    const long nitems = (long)T * (KP / 2);
+    reduce_features_strip_finalize_kernel<KT><<<(int)((nitems + 31) / 32), 256, 0, stream>>>(
+        (const double*)workspace, T, nstrips, k, out, ldo, flags);
+    CDR_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+size_t reduce_features_tma_workspace_bytes(int T, int d, int k)
+{
+    const int dpad = (d + 31) / 32 * 32;
+    int TC, nstrips;
+    strip_geometry(dpad, kFsTcMax, &TC, &nstrips);
+    const int kp = (k + 7) / 8 * 8;
+    if (k > 16 || (long)nstrips * kp * 10 > (long)dpad) return 0;
+    return (size_t)nstrips * T * kp * sizeof(double);
+}
+
+int run_reduce_features_tma(const double* M, long ldm, const double* X, long ldx, int T, int d,
+                            int k, double* out, long ldo, void* workspace, size_t workspace_bytes,
+                            const cdr_flags* flags, cudaStream_t stream)
+{
+    int TC, nstrips;
+    if (!features_strip_ok(M, ldm, X, ldx, T, d, k, &TC, &nstrips)) return CDR_TMA_NOT_APPLICABLE;
+    const int dpad = (d + 31) / 32 * 32;
+    if (k <= 8)
+        return launch_features_strip<1>(M, ldm, X, ldx, T, dpad, k, TC, nstrips, out, ldo, workspace,
+                                        workspace_bytes, flags, stream);
+    return launch_features_strip<2>(M, ldm, X, ldx, T, dpad, k, TC, nstrips, out, ldo, workspace,
+                                    workspace_bytes, flags, stream);
+}
+
+}  // namespace cdr

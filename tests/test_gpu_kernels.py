@@ -323,3 +323,42 @@ def test_furthest_sum_large_random_vs_oracle():
     D = np.sqrt(np.maximum(((P[:, None, :] - P[None, :, :]) ** 2).sum(-1), 0))
     ref = orc.furthest_sum(D, 8, 11, [], 10)
     assert np.array_equal(furthest_sum(D, 8, 11, [], 10), np.asarray(ref, dtype=np.int64))
+
+
+# ---------------------------------------------------------------- TMA-pipelined passes
+@pytest.mark.parametrize('T,d,k', [(300, 9000, 8), (1000, 5000, 16), (130, 20000, 5),
+                                   (257, 4800, 20), (70, 6016, 32), (1620, 44000, 8),
+                                   (64, 9472, 1), (203, 12345, 3)])
+def test_tma_streaming_passes(T, d, k, monkeypatch):
+    """Shapes that take the cp.async.bulk + mbarrier pipeline: against NumPy and against
+    the direct-load kernels (CDR_DISABLE_TMA=1)."""
+    rs = np.random.RandomState(T + d + k)
+    X = rs.standard_normal((T, d))
+    Z = rs.uniform(size=(T, k))
+    L = rs.standard_normal((k, T))
+    E = rs.standard_normal((k, k))
+    M = rs.standard_normal((k, d))
+    Xd, Zd, Ld, Ed, Md = (be.to_device_padded(X), be.to_device(Z), be.to_device_padded(L),
+                          be.to_device(E), be.to_device_padded(M))
+    ws = be.Workspace(T, d, k)
+    res = {}
+    for mode in ('tma', 'direct'):
+        monkeypatch.setenv('CDR_DISABLE_TMA', '1' if mode == 'direct' else '0')
+        o1, o2 = be.zeros(k, Xd.stride(0)), be.zeros(k, Xd.stride(0))
+        o3 = be.zeros(k, be.round_up(T))
+        be.reduce_samples(Ld, Ld.stride(0), 1, Xd, T, d, k, o1, ws)
+        be.reduce_samples(Zd, 1, k, Xd, T, d, k, o2, ws, E=Ed)
+        be.reduce_features(Md, Xd, T, d, k, o3, ws)
+        torch.cuda.synchronize()
+        res[mode] = (be.to_host(o1), be.to_host(o2), be.to_host(o3, k, T))
+        close(res[mode][0][:, :d], L.dot(X), rtol=1e-12, atol=1e-10)
+        assert np.all(res[mode][0][:, d:] == 0)
+        close(res[mode][1][:, :d], E.dot(Z.T.dot(X)), rtol=1e-11, atol=1e-9)
+        close(res[mode][2], M.dot(X.T), rtol=1e-12, atol=1e-10)
+    for a, b in zip(res['tma'], res['direct']):
+        close(a, b, rtol=1e-12, atol=1e-10)
+    # deterministic: a second run is bit-identical
+    monkeypatch.setenv('CDR_DISABLE_TMA', '0')
+    o3b = be.zeros(k, be.round_up(T))
+    be.reduce_features(Md, Xd, T, d, k, o3b, ws)
+    assert np.array_equal(be.to_host(o3b, k, T), res['tma'][2])

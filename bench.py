@@ -121,10 +121,12 @@ def make_problem(args, rank=0, world=1):
     X = synthetic_field(T, d, seed=rank)
     rs = np.random.RandomState(1000 + rank)
     if args.workload == 'gpnh':
-        W0 = np.sqrt(np.abs(X).mean() / k) * np.random.RandomState(0).randn(d, k)
+        # the dictionary is replicated: every rank draws the same one
+        W0 = np.sqrt(0.4 / k) * np.random.RandomState(0).randn(d, k)
         Z0 = orc.right_stochastic_matrix((T, k), rs)
         return X, Z0, W0
-    C0 = orc.right_stochastic_matrix((k, T), rs)
+    # the dictionary (k x total samples) is replicated; the weights are this rank's rows
+    C0 = orc.right_stochastic_matrix((k, T * world), np.random.RandomState(7))
     Z0 = orc.right_stochastic_matrix((T, k), rs)
     return X, Z0, C0
 

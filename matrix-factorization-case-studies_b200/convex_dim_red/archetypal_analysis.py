@@ -18,6 +18,7 @@ import numpy as np
 from sklearn.utils import check_array, check_random_state
 
 from . import _backend as be
+from ._dist import Comm, shard_bounds, shard_sizes
 from .furthest_sum import dissimilarity_from_gram_device, furthest_sum_device
 from .spg import spg
 from .stochastic_matrices import right_stochastic_matrix
@@ -67,11 +68,22 @@ class _AaEngine:
                  require_monotonic_cost_decrease=True, weights_solver_kwargs=None,
                  dictionary_solver_kwargs=None, scale_factors_solver_kwargs=None,
                  update_weights=True, update_dictionary=True, update_scale_factors=True,
-                 trace_data=None, data_device=None):
-        be.require_cuda()
+                 trace_data=None, data_device=None, comm=None):
+        torch = be.require_cuda()
         self.mode = mode
-        self.T = weights.shape[0]
+        # sample-sharded fit: `data` / `weights` hold this rank's rows; the dictionary and
+        # every k x T quantity are replicated (T = total number of samples)
+        self.comm = comm if comm is not None else Comm(enabled=False)
+        if self.comm.enabled and mode != 'feature':
+            raise NotImplementedError('sample sharding is implemented for feature-space AA')
+        self.Tl = weights.shape[0]
         self.k = weights.shape[1]
+        self.T = np.asarray(dictionary).shape[1]
+        self.sizes = shard_sizes(self.T, self.comm.world)
+        self.lo = shard_bounds(self.T, self.comm.world, self.comm.rank)[0]
+        if self.sizes[self.comm.rank] != self.Tl:
+            raise ValueError('local weights have %d rows, expected %d of %d'
+                             % (self.Tl, self.sizes[self.comm.rank], self.T))
         T, k = self.T, self.k
         if k > be.MAX_COMPONENTS:
             raise ValueError('n_components > %d is not supported by the B200 build'
@@ -108,13 +120,18 @@ class _AaEngine:
             self.tmp_kd = be.zeros(k, self.ldx)
         else:
             self.Zt = be.zeros(k, ldt)
-        self.ws = be.Workspace(T, self.d, k)
+        if self.comm.enabled:
+            self.loc_kt = be.zeros(k, be.round_up(self.Tl))
+            self.gather_scratch = be.zeros(self.comm.world + 1, k, max(self.sizes))
+        self.ws = be.Workspace(max(T, self.Tl), self.d, k)
         self.state = be.DeviceState(tolerance, max_iterations, stopping_criterion,
                                     require_monotonic_cost_decrease)
         if trace_data is None:
             if mode == 'feature':
                 # archetypal_analysis.py:552 forms X X' only for its trace
-                trace_data = float(be.frobenius_sq(self.X, T, self.d).item())
+                tr = be.frobenius_sq(self.X, self.Tl, self.d)
+                self.comm.allreduce_sum(tr)
+                trace_data = float(tr.item())
             else:
                 trace_data = float(np.asarray(data).trace())
         self.trace_data = float(trace_data)
@@ -131,33 +148,44 @@ class _AaEngine:
         self._first_dictionary_update = True
 
     # -- products with K ----------------------------------------------------
+    def _features_to_columns(self, out, flags):
+        """(tmp_kd) X' for this rank's samples, placed in (all-gathered into) `out`."""
+        Tl, d, k = self.Tl, self.d, self.k
+        if not self.comm.enabled:
+            be.reduce_features(self.tmp_kd, self.X, Tl, d, k, out, self.ws, flags)
+            return
+        self.comm.allreduce_sum(self.tmp_kd)
+        be.reduce_features(self.tmp_kd, self.X, Tl, d, k, self.loc_kt, self.ws, flags)
+        self.comm.allgather_columns(self.loc_kt, out, self.sizes, self.gather_scratch)
+
     def apply_left(self, L, out, flags):
         """out = L K for a k x T matrix L (dictionary.dot(K) or (L X) X')."""
-        T, d, k = self.T, self.d, self.k
+        Tl, d, k = self.Tl, self.d, self.k
         if self.mode == 'feature':
-            be.reduce_samples(L, L.stride(0), 1, self.X, T, d, k, self.tmp_kd, self.ws,
+            Lloc = L[:, self.lo:] if self.lo else L
+            be.reduce_samples(Lloc, L.stride(0), 1, self.X, Tl, d, k, self.tmp_kd, self.ws,
                               flags=flags)
-            be.reduce_features(self.tmp_kd, self.X, T, d, k, out, self.ws, flags)
+            self._features_to_columns(out, flags)
         else:
-            be.reduce_samples(L, L.stride(0), 1, self.X, T, T, k, out, self.ws, flags=flags)
+            be.reduce_samples(L, L.stride(0), 1, self.X, Tl, Tl, k, out, self.ws, flags=flags)
 
     def apply_right(self, flags):
         """KZt = (K Z)' (K.dot(weights) or X (X' Z))."""
-        T, d, k = self.T, self.d, self.k
+        Tl, d, k = self.Tl, self.d, self.k
         if self.mode == 'feature':
-            be.reduce_samples(self.Z, 1, k, self.X, T, d, k, self.tmp_kd, self.ws, flags=flags)
-            be.reduce_features(self.tmp_kd, self.X, T, d, k, self.KZt, self.ws, flags)
+            be.reduce_samples(self.Z, 1, k, self.X, Tl, d, k, self.tmp_kd, self.ws, flags=flags)
+            self._features_to_columns(self.KZt, flags)
         else:
-            self.Zt[:, :T].copy_(self.Z.t())
-            be.reduce_features(self.Zt, self.X, T, T, k, self.KZt, self.ws, flags)
+            self.Zt[:, :Tl].copy_(self.Z.t())
+            be.reduce_features(self.Zt, self.X, Tl, Tl, k, self.KZt, self.ws, flags)
 
     # -- small products -----------------------------------------------------
     def _desc(self, A, B, out):
         return (A, A.stride(0), 1, self.k, B, B.stride(0), 1, self.k, self.T, out, 1.0, 0)
 
     def _desc_ZtZ(self):
-        k, T = self.k, self.T
-        return (self.Z, 1, k, k, self.Z, 1, k, k, T, self.ZtZ, 1.0, 0)
+        k = self.k
+        return (self.Z, 1, k, k, self.Z, 1, k, k, self.Tl, self.ZtZ, 1.0, 0)
 
     def _cost_check(self, stage, end):
         be.check(self.lib.cdr_aa_cost_check(ctypes.byref(self.buf), stage, int(end),
@@ -172,6 +200,7 @@ class _AaEngine:
             self.apply_right(fl)
         be.small_gram([self._desc_ZtZ(), self._desc(self.CK, self.C, self.CKCt),
                        self._desc(self.C, self.KZt, self.CKZ)], self.ws, fl)
+        self.comm.allreduce_sum(self.ZtZ)
 
     def initial_cost(self):
         self.precompute()
@@ -228,10 +257,12 @@ class _AaEngine:
         """_update_kernel_aa_weights and the recomputes that follow it
         (archetypal_analysis.py:369-396, 489-503, 632-652)."""
         fl = self.state.ptr
-        be.quad_simplex_spg_batched(self.CKCt, self.alpha, self.CK, 1, self.ldt, self.Z,
-                                    self.T, self.k, self.w_params, flags=fl)
+        CKloc = self.CK[:, self.lo:] if self.lo else self.CK
+        be.quad_simplex_spg_batched(self.CKCt, self.alpha, CKloc, 1, self.ldt, self.Z,
+                                    self.Tl, self.k, self.w_params, flags=fl)
         self.apply_right(fl)
         be.small_gram([self._desc_ZtZ(), self._desc(self.C, self.KZt, self.CKZ)], self.ws, fl)
+        self.comm.allreduce_sum(self.ZtZ)
         if stage is not None:
             self._cost_check(stage, end)
 
@@ -283,7 +314,8 @@ class _AaEngine:
         torch = be.torch_mod()
         if use_graph is None:
             use_graph = not be.graphs_disabled()
-        use_graph = use_graph and self.graph_capturable() and not verbose
+        use_graph = (use_graph and self.graph_capturable() and not verbose and
+                     not self.comm.enabled)
         be.trace('aa: engine ready')
         self.initial_cost()
         be.trace('aa: initial cost')
@@ -574,7 +606,7 @@ def _iterate(data, weights, dictionary, alpha, mode, delta, update_weights,
         scale_factors_solver_kwargs=kwargs.get('scale_factors_solver_kwargs', {}),
         update_weights=update_weights, update_dictionary=update_dictionary,
         update_scale_factors=update_scale_factors, trace_data=kwargs.get('trace_data'),
-        data_device=kwargs.get('data_device'))
+        data_device=kwargs.get('data_device'), comm=kwargs.get('comm'))
     eng.run(verbose=verbose, label='Kernel AA' if mode == 'kernel' else 'AA')
     new_weights = eng.weights() if update_weights else weights
     new_dictionary = eng.dictionary() if update_dictionary else dictionary

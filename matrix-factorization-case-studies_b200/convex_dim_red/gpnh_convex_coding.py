@@ -17,6 +17,7 @@ import numpy as np
 from sklearn.utils import check_array, check_random_state
 
 from . import _backend as be
+from ._dist import Comm
 from .furthest_sum import dissimilarity_from_gram_device, furthest_sum_device
 from .stochastic_matrices import right_stochastic_matrix
 from .validation_utils import check_array_shape, check_unit_axis_sums
@@ -46,8 +47,10 @@ class _GpnhEngine:
                  max_iterations=1000, stopping_criterion='abs_delta_f',
                  require_monotonic_cost_decrease=True, weights_solver_kwargs=None,
                  update_dictionary=True, update_weights=True, trace_XtX=None,
-                 X_device=None):
+                 X_device=None, comm=None):
         torch = be.require_cuda()
+        # sample-sharded fit: X / weights hold this rank's rows, the dictionary is replicated
+        self.comm = comm if comm is not None else Comm(enabled=False)
         self.T, self.d = X.shape
         self.k = weights.shape[1]
         if self.k > be.MAX_COMPONENTS:
@@ -64,9 +67,11 @@ class _GpnhEngine:
         self.Z = be.to_device(weights)
         self.WT = be.to_device_padded(np.ascontiguousarray(np.asarray(dictionary).T))
         self.XWt = be.zeros(k, self.ldt)
-        self.ZtZ = be.zeros(k, k)
+        # the two statistics that reduce over samples share one buffer (one all-reduce)
+        self.stats = be.zeros(2, k, k)
+        self.ZtZ = self.stats[0]
+        self.XWtZ = self.stats[1]
         self.WtW = be.zeros(k, k)
-        self.XWtZ = be.zeros(k, k)
         self.REG = be.zeros(k, k)
         self.P = be.zeros(k, k)
         self.ws = be.Workspace(T, d, k)
@@ -74,8 +79,13 @@ class _GpnhEngine:
                                     require_monotonic_cost_decrease)
         if trace_XtX is None:
             # gpnh_convex_coding.py:302 forms the d x d product only for its trace
-            trace_XtX = float(be.frobenius_sq(self.X, T, d).item())
+            tr = be.frobenius_sq(self.X, T, d)
+            self.comm.allreduce_sum(tr)
+            trace_XtX = float(tr.item())
         self.state.write_field('trace_data', float(trace_XtX))
+        n_tot = torch.tensor([T], dtype=torch.int64, device='cuda')
+        self.comm.allreduce_sum(n_tot)
+        self.T_total = int(n_tot.item())
         self.lib = be.library()
         self._graph = None
 
@@ -100,8 +110,8 @@ class _GpnhEngine:
         be.check(self.lib.cdr_gpnh_cost_check(
             self.state.ptr, self.state.cost_deltas.data_ptr(), self.XWtZ.data_ptr(),
             self.ZtZ.data_ptr(), self.WtW.data_ptr(),
-            self.REG.data_ptr() if with_reg else None, self.k, self.T, self.d, self.lambda_W,
-            stage, int(end), be.stream_ptr()), 'cdr_gpnh_cost_check')
+            self.REG.data_ptr() if with_reg else None, self.k, self.T_total, self.d,
+            self.lambda_W, stage, int(end), be.stream_ptr()), 'cdr_gpnh_cost_check')
 
     # -- pieces of the loop -------------------------------------------------
     def initial_cost(self):
@@ -112,6 +122,7 @@ class _GpnhEngine:
         if self.lambda_W != 0:
             descs.append(self._desc_REG())
         be.small_gram(descs, self.ws, flags)
+        self.comm.allreduce_sum(self.stats)
         self._cost_check(0, False, self.lambda_W != 0)
 
     def dictionary_step(self, stage=2, end=False, flags=True):
@@ -120,14 +131,16 @@ class _GpnhEngine:
         fl = self.state.ptr if flags else None
         T, d, k = self.T, self.d, self.k
         be.check(self.lib.cdr_gpnh_solve_matrix(
-            self.ZtZ.data_ptr(), k, T, d, self.lambda_W, self.P.data_ptr(), None, 0, fl,
-            be.stream_ptr()), 'cdr_gpnh_solve_matrix')
+            self.ZtZ.data_ptr(), k, self.T_total, d, self.lambda_W, self.P.data_ptr(), None, 0,
+            fl, be.stream_ptr()), 'cdr_gpnh_solve_matrix')
         be.reduce_samples(self.Z, 1, k, self.X, T, d, k, self.WT, self.ws, E=self.P, flags=fl)
+        self.comm.allreduce_sum(self.WT)          # W' = P sum_g Z_g' X_g
         be.reduce_features(self.WT, self.X, T, d, k, self.XWt, self.ws, fl)
         descs = [self._desc_WtW(), self._desc_XWtZ()]
         if self.lambda_W != 0:
             descs.append(self._desc_REG())
         be.small_gram(descs, self.ws, fl)
+        self.comm.allreduce_sum(self.XWtZ)
         if stage is not None:
             self._cost_check(stage, end, self.lambda_W != 0)
 
@@ -137,6 +150,7 @@ class _GpnhEngine:
         be.quad_simplex_spg_batched(self.WtW, None, self.XWt, 1, self.ldt, self.Z, self.T,
                                     self.k, self.params, flags=fl)
         be.small_gram([self._desc_ZtZ(), self._desc_XWtZ()], self.ws, fl)
+        self.comm.allreduce_sum(self.stats)
         if stage is not None:
             self._cost_check(stage, end, False)
 
@@ -151,8 +165,10 @@ class _GpnhEngine:
     def run(self, verbose=0, use_graph=None):
         torch = be.torch_mod()
         if use_graph is None:
-            use_graph = not be.graphs_disabled()
+            use_graph = not be.graphs_disabled() and not self.comm.enabled
+        be.trace('gpnh: engine ready')
         self.initial_cost()
+        be.trace('gpnh: initial cost')
         max_it = self.state.max_iterations
         start = time.perf_counter()
         launched = 0
@@ -169,7 +185,9 @@ class _GpnhEngine:
         graph = None
         while not st.done and launched < max_it:
             if use_graph and graph is None and not verbose:
+                be.trace('gpnh: first iteration')
                 graph = be.capture_graph(self.iteration)
+                be.trace('gpnh: graph capture')
             n = min(chunk, max_it - launched)
             for _ in range(n):
                 if graph is not None:
@@ -186,6 +204,7 @@ class _GpnhEngine:
         torch.cuda.synchronize()
         elapsed = time.perf_counter() - start
         st = self.state.read()
+        be.trace('gpnh: remaining iterations')
         if st.error_stage:
             raise RuntimeError('factorization cost increased after {} update'.format(
                 _STAGES[st.error_stage]))
@@ -300,6 +319,7 @@ def _iterate_gpnh_convex_coding(X, weights, dictionary, lambda_W=0,
         raise TypeError("_update_gpnh_dictionary() got an unexpected keyword argument '%s'"
                         % next(iter(kwargs['dictionary_solver_kwargs'])))
     X = np.asarray(X, dtype=np.float64)
+    be.trace('gpnh: enter _iterate')
     engine = _GpnhEngine(
         X, weights, dictionary, lambda_W=lambda_W, tolerance=tolerance,
         max_iterations=max_iterations,
@@ -307,10 +327,12 @@ def _iterate_gpnh_convex_coding(X, weights, dictionary, lambda_W=0,
         require_monotonic_cost_decrease=kwargs.get('require_monotonic_cost_decrease', True),
         weights_solver_kwargs=kwargs.get('weights_solver_kwargs', {}),
         update_dictionary=update_dictionary, update_weights=update_weights,
-        trace_XtX=kwargs.get('trace_XtX'), X_device=kwargs.get('X_device'))
+        trace_XtX=kwargs.get('trace_XtX'), X_device=kwargs.get('X_device'),
+        comm=kwargs.get('comm'))
     engine.run(verbose=verbose)
     new_weights = engine.weights() if update_weights else weights
     new_dictionary = engine.dictionary() if update_dictionary else dictionary
+    be.trace('gpnh: results to host')
     return (new_weights, new_dictionary, engine.cost, engine.n_iter,
             engine.avg_time_per_iter, engine.cost_deltas)
 

@@ -1,0 +1,71 @@
+"""Sample-sharded (N > 1) path: world_size-2 gloo test on CPU, and -- when two GPUs are
+visible -- the sharded engines over NCCL against a single-GPU run of the same problem."""
+
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+WORKER = os.path.join(ROOT, 'tests', '_dist_worker.py')
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _launch(mode, out, nproc=2, timeout=600):
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(nproc),
+           '--master-addr', '127.0.0.1', '--master-port', str(_free_port()), WORKER,
+           '--mode', mode, '--out', out]
+    env = dict(os.environ, OMP_NUM_THREADS='2')
+    res = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                         timeout=timeout)
+    assert res.returncode == 0, res.stdout.decode()[-4000:]
+
+
+def test_shard_bounds():
+    from convex_dim_red._dist import shard_bounds, shard_sizes
+    for n, w in ((10, 3), (1620, 8), (7, 8), (1, 1)):
+        spans = [shard_bounds(n, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert shard_sizes(n, w) == [hi - lo for lo, hi in spans]
+
+
+def test_sharded_algebra_gloo_world2(tmp_path):
+    out = str(tmp_path / 'gloo.npz')
+    _launch('gloo', out)
+    assert np.load(out)['ok'][0] == 1
+
+
+@pytest.mark.gpu
+def test_sharded_engines_nccl_world2(tmp_path):
+    torch = pytest.importorskip('torch')
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from _dist_worker import problem
+    from convex_dim_red import archetypal_analysis as aa
+    from convex_dim_red import gpnh_convex_coding as gp
+    out = str(tmp_path / 'nccl.npz')
+    _launch('nccl', out)
+    got = np.load(out)
+    X, Z0, W0, C0 = problem(T=403, d=2600, k=8)
+    g = gp._iterate_gpnh_convex_coding(X, Z0.copy(), W0.copy(), lambda_W=0.2, tolerance=1e-12,
+                                       max_iterations=6)
+    a = aa._iterate_aa(X, Z0.copy(), C0.copy(), np.ones(8), tolerance=1e-12, max_iterations=6,
+                       dictionary_solver_kwargs=dict(max_iterations=2))
+    assert int(got['gn']) == g[3] and int(got['an']) == a[4]
+    np.testing.assert_allclose(got['gcost'], g[2], rtol=1e-9)
+    np.testing.assert_allclose(got['gZ'], g[0], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(got['gW'], g[1], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(got['acost'], a[3], rtol=1e-9)
+    np.testing.assert_allclose(got['aZ'], a[0], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(got['aC'], a[1], rtol=0, atol=2e-5)

@@ -10,6 +10,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
     --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 $CMD > gpurun_out/plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on \
-    -k regex:'reduce_(samples|features)_kernel|qp_batched_kernel' -s 4 -c 6 \
+    -k regex:'reduce_samples_tma_kernel|reduce_features_strip_kernel|qp_batched_kernel' -s 3 -c 6 \
     -o gpurun_out/prof $CMD > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out

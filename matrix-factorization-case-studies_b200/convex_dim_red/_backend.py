@@ -244,8 +244,9 @@ class Workspace:
         self.nbytes_features = lib.cdr_reduce_features_workspace_bytes(T, d, k)
         self.nbytes_gram = lib.cdr_small_gram_workspace_bytes()
         n = max(self.nbytes_samples, self.nbytes_features, 8)
-        self.stream_ws = torch.zeros(n // 8 + 1, dtype=torch.float64, device='cuda')
-        self.gram_ws = torch.zeros(self.nbytes_gram // 8 + 1, dtype=torch.float64, device='cuda')
+        # scratch is fully written before it is read: no need to clear it
+        self.stream_ws = torch.empty(n // 8 + 1, dtype=torch.float64, device='cuda')
+        self.gram_ws = torch.empty(self.nbytes_gram // 8 + 1, dtype=torch.float64, device='cuda')
 
     def ensure(self, T, d, k):
         lib = library()

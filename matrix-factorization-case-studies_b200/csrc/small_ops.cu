@@ -8,8 +8,10 @@ namespace cdr {
 // ======================================================================
 // batched small products
 // ======================================================================
-constexpr int kGramMaxBlocks = 128;
-constexpr int kGramTile = 32;
+constexpr int kGramMaxBlocks = 512;
+constexpr int kGramTile = 32;           // tile width for k > 16
+constexpr int kGramTileWide = 128;      // tile width for k <= 16 (one tile per CTA)
+constexpr int kGramTileDoubles = 2112;  // max(16 * (128 + 1), 64 * (32 + 1))
 constexpr int kGramMaxPairs = CDR_MAX_COMPONENTS * CDR_MAX_COMPONENTS;
 
 struct GramBatch {
@@ -26,16 +28,18 @@ small_gram_partial_kernel(GramBatch batch, double* __restrict__ part, const cdr_
     const cdr_small_gram_desc& ds = batch.d[blockIdx.y];
     const int nblk = batch.nblk[blockIdx.y];
     if ((int)blockIdx.x >= nblk) return;
-    __shared__ double As[CDR_MAX_COMPONENTS][kGramTile + 1];
-    __shared__ double Bs[CDR_MAX_COMPONENTS][kGramTile + 1];
+    __shared__ double As[kGramTileDoubles];
+    __shared__ double Bs[kGramTileDoubles];
     __shared__ double red[256];
 
     const int ka = ds.ka, kb = ds.kb, npairs = ka * kb;
+    const int tw = (ka <= 16 && kb <= 16) ? kGramTileWide : kGramTile;
+    const int ld = tw + 1;
     const int nsub = (npairs <= 64) ? 4 : (npairs <= 128) ? 2 : 1;
     const int slots = 256 / nsub;                  // pair slots per pass
     const int slot = threadIdx.x % slots, sub = threadIdx.x / slots;
     int chunk = (ds.n + nblk - 1) / nblk;
-    chunk = (chunk + kGramTile - 1) / kGramTile * kGramTile;
+    chunk = (chunk + tw - 1) / tw * tw;
     const int n0 = blockIdx.x * chunk;
     const int n1 = min(ds.n, n0 + chunk);
 
@@ -43,15 +47,15 @@ small_gram_partial_kernel(GramBatch batch, double* __restrict__ part, const cdr_
 #pragma unroll
     for (int s = 0; s < kGramMaxPairs / 256; ++s) acc[s] = 0.0;
 
-    for (int nb = n0; nb < n1; nb += kGramTile) {
-        const int w = min(kGramTile, n1 - nb);
-        for (int idx = threadIdx.x; idx < ka * kGramTile; idx += 256) {
-            const int i = idx / kGramTile, cix = idx % kGramTile;
-            As[i][cix] = (cix < w) ? ds.A[(long)i * ds.sAi + (long)(nb + cix) * ds.sAn] : 0.0;
+    for (int nb = n0; nb < n1; nb += tw) {
+        const int w = min(tw, n1 - nb);
+        for (int idx = threadIdx.x; idx < ka * tw; idx += 256) {
+            const int i = idx / tw, cix = idx % tw;
+            As[i * ld + cix] = (cix < w) ? ds.A[(long)i * ds.sAi + (long)(nb + cix) * ds.sAn] : 0.0;
         }
-        for (int idx = threadIdx.x; idx < kb * kGramTile; idx += 256) {
-            const int j = idx / kGramTile, cix = idx % kGramTile;
-            Bs[j][cix] = (cix < w) ? ds.B[(long)j * ds.sBj + (long)(nb + cix) * ds.sBn] : 0.0;
+        for (int idx = threadIdx.x; idx < kb * tw; idx += 256) {
+            const int j = idx / tw, cix = idx % tw;
+            Bs[j * ld + cix] = (cix < w) ? ds.B[(long)j * ds.sBj + (long)(nb + cix) * ds.sBn] : 0.0;
         }
         __syncthreads();
 #pragma unroll
@@ -59,12 +63,14 @@ small_gram_partial_kernel(GramBatch batch, double* __restrict__ part, const cdr_
             const int p = slot + s * slots;
             if (p < npairs && (s == 0 || nsub == 1)) {
                 const int i = p / kb, j = p % kb;
+                const double* ar = As + i * ld;
+                const double* br = Bs + j * ld;
                 double a = acc[s];
                 if (ds.mode == 0) {
-                    for (int cix = sub; cix < kGramTile; cix += nsub) a = fma(As[i][cix], Bs[j][cix], a);
+                    for (int cix = sub; cix < tw; cix += nsub) a = fma(ar[cix], br[cix], a);
                 } else {
-                    for (int cix = sub; cix < kGramTile; cix += nsub) {
-                        const double df = As[i][cix] - Bs[j][cix];
+                    for (int cix = sub; cix < tw; cix += nsub) {
+                        const double df = ar[cix] - br[cix];
                         a = fma(df, df, a);
                     }
                 }
@@ -146,12 +152,82 @@ gpnh_solve_matrix_kernel(const double* __restrict__ ZtZ, int k, double inv_n, do
     __shared__ int rotated;
     __shared__ double inv_eig[CDR_MAX_COMPONENTS];
 
+    __shared__ int chol_ok;
+    __shared__ double chol_tmp[CDR_MAX_COMPONENTS];
+
     const int tid = threadIdx.x;
     for (int idx = tid; idx < k * k; idx += blockDim.x) {
         const int i = idx / k, j = idx % k;
         double v = ZtZ[idx] * inv_n;
         if (k > 1) v += lambda_W * gw_prefactor * ((i == j ? (double)k : 0.0) - 1.0);
         A[i * kJacLd + j] = v;
+        V[i * kJacLd + j] = v;            // Cholesky works in V; Jacobi re-initialises it
+    }
+    __syncthreads();
+
+    // ---- fast path: the matrix is symmetric positive definite and reasonably conditioned
+    // (the usual case): P = A^-1 by Cholesky, a few microseconds instead of ~50 for the
+    // Jacobi sweeps.  Any pivot below 1e-10 * max diag falls through to the
+    // pseudo-inverse, which reproduces lstsq's minimum-norm solution for singular Z'Z.
+    if (tid < 32) {
+        const int lane = tid;
+        double dmax = 0.0;
+        for (int i = 0; i < k; ++i) dmax = fmax(dmax, V[i * kJacLd + i]);
+        const double thr = 1e-10 * dmax;
+        bool ok = dmax > 0.0;
+        for (int j = 0; j < k && ok; ++j) {
+            for (int i = j + lane; i < k; i += 32) {
+                double sacc = V[i * kJacLd + j];
+                for (int q = 0; q < j; ++q) sacc = fma(-V[i * kJacLd + q], V[j * kJacLd + q], sacc);
+                chol_tmp[i] = sacc;
+            }
+            __syncwarp();
+            const double dj = chol_tmp[j];
+            if (!(dj > thr)) {
+                ok = false;
+            } else {
+                const double root = sqrt(dj);
+                for (int i = j + lane; i < k; i += 32)
+                    V[i * kJacLd + j] = (i == j) ? root : chol_tmp[i] / root;
+            }
+            __syncwarp();
+        }
+        if (ok) {
+            // columns of L^-1 by forward substitution (one column per lane), stored in A's
+            // upper part is not safe (A may still be needed) -> reuse chol-free rows of V:
+            // L^-1 overwrites the strictly-upper triangle + a separate diagonal pass
+            for (int c = lane; c < k; c += 32) {
+                // y = L^-1 e_c, kept in the upper triangle V[c][i] (i >= c)
+                double ycc = 1.0 / V[c * kJacLd + c];
+                for (int i = c + 1; i < k; ++i) {
+                    double sacc = V[i * kJacLd + c] * ycc;
+                    for (int q = c + 1; q < i; ++q) sacc = fma(V[i * kJacLd + q], V[c * kJacLd + q], sacc);
+                    V[c * kJacLd + i] = -sacc / V[i * kJacLd + i];
+                }
+                chol_tmp[c] = ycc;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) chol_ok = ok ? 1 : 0;
+    }
+    __syncthreads();
+    if (chol_ok) {
+        // (L^-1)[i][c] = V[c][i] for i > c, chol_tmp[c] for i == c;  P = L^-T L^-1
+        for (int idx = tid; idx < k * k; idx += blockDim.x) {
+            const int a = idx / k, b = idx % k;
+            const int lo = a > b ? a : b;
+            double sacc = 0.0;
+            for (int i = lo; i < k; ++i) {
+                const double la = (i == a) ? chol_tmp[a] : V[a * kJacLd + i];
+                const double lb = (i == b) ? chol_tmp[b] : V[b * kJacLd + i];
+                sacc = fma(la, lb, sacc);
+            }
+            P[idx] = sacc * inv_n;
+        }
+        return;
+    }
+    for (int idx = tid; idx < k * k; idx += blockDim.x) {
+        const int i = idx / k, j = idx % k;
         V[i * kJacLd + j] = (i == j) ? 1.0 : 0.0;
     }
     __syncthreads();
@@ -343,7 +419,7 @@ extern "C" int cdr_small_gram(const cdr_small_gram_desc* descs, int count, void*
         CDR_CHECK_ARG(descs[i].ka >= 1 && descs[i].kb >= 1 && descs[i].n >= 0);
         if (descs[i].ka > CDR_MAX_COMPONENTS || descs[i].kb > CDR_MAX_COMPONENTS)
             return CDR_ERR_UNSUPPORTED;
-        int nb = (descs[i].n + 127) / 128;
+        int nb = (descs[i].n + kGramTileWide - 1) / kGramTileWide;
         if (nb < 1) nb = 1;
         if (nb > kGramMaxBlocks) nb = kGramMaxBlocks;
         batch.nblk[i] = nb;

@@ -346,13 +346,26 @@ frobenius_partial_kernel(const double* __restrict__ X, long ldx, int T, int d, d
 {
     __shared__ double scratch[32];
     double s[1] = {0.0};
-    // one row at a time per CTA: coalesced, fixed assignment => deterministic
+    // one row at a time per CTA: coalesced 16-byte loads, fixed assignment => deterministic
+    // (rows are 256-byte aligned and zero padded, so the padded tail may be read)
+    const int d2 = (d + 1) / 2;
     for (int t = blockIdx.x; t < T; t += gridDim.x) {
-        const double* row = X + (long)t * ldx;
-        for (int f = threadIdx.x; f < d; f += blockDim.x) {
-            const double v = row[f];
-            s[0] = fma(v, v, s[0]);
+        const double2* row = reinterpret_cast<const double2*>(X + (long)t * ldx);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int f = threadIdx.x;
+        for (; f + 256 < d2; f += 512) {
+            const double2 v = row[f], w = row[f + 256];
+            a0 = fma(v.x, v.x, a0);
+            a1 = fma(v.y, v.y, a1);
+            a2 = fma(w.x, w.x, a2);
+            a3 = fma(w.y, w.y, a3);
         }
+        for (; f < d2; f += 256) {
+            const double2 v = row[f];
+            a0 = fma(v.x, v.x, a0);
+            if (2 * f + 1 < d) a1 = fma(v.y, v.y, a1);
+        }
+        s[0] += (a0 + a1) + (a2 + a3);
     }
     block_sum<1>(s, scratch);
     if (threadIdx.x == 0) part[blockIdx.x] = s[0];
@@ -513,7 +526,7 @@ extern "C" size_t cdr_frobenius_workspace_bytes(void) { return kFrobBlocks * siz
 extern "C" int cdr_frobenius_sq(const double* X, long ldx, int T, int d, double* out,
                                 void* workspace, size_t workspace_bytes, cdr_stream_t stream)
 {
-    CDR_CHECK_ARG(T >= 1 && d >= 1 && ldx >= d);
+    CDR_CHECK_ARG(T >= 1 && d >= 1 && ldx >= d && ldx % 2 == 0);
     if (workspace == nullptr || workspace_bytes < kFrobBlocks * sizeof(double))
         return CDR_ERR_WORKSPACE;
     cudaStream_t s = (cudaStream_t)stream;

@@ -102,23 +102,35 @@ reduce_samples_tma_kernel(const double* __restrict__ Lp, long sLi, long sLt,
             for (int mt = 0; mt < KT; ++mt)
                 acc[u][mt][0][0] = acc[u][mt][0][1] = acc[u][mt][1][0] = acc[u][mt][1][1] = 0.0;
 
+        // left-operand fragments L[i][t] are prefetched one stage ahead into registers: a
+        // load issued right before use stalls the first DMMA of every stage on an L2 round
+        // trip (27 % of the stall samples in profiles/r01b)
+        double a_next[kSampKS][KT];
+        auto load_left = [&](int rt_load) {
+#pragma unroll
+            for (int ks = 0; ks < kSampKS; ++ks) {
+                const int tt = rt_load * kSampTR + 4 * ks + lr;
+#pragma unroll
+                for (int mt = 0; mt < KT; ++mt) {
+                    const int i = mt * 8 + lc;
+                    a_next[ks][mt] = (tt < T && i < k) ? Lp[(long)i * sLi + (long)tt * sLt] : 0.0;
+                }
+            }
+        };
+        load_left(0);
         for (int rt = 0; rt < ntiles; ++rt, ++it) {
             const int s = it % stages;
             const uint32_t ph = (uint32_t)(it / stages) & 1u;
             const int t0 = rt * kSampTR;
-            // left-operand fragments of the stage's k-steps, fetched before the wait
             double a[kSampKS][KT];
             bool rowok[kSampKS];
 #pragma unroll
             for (int ks = 0; ks < kSampKS; ++ks) {
-                const int tt = t0 + 4 * ks + lr;
-                rowok[ks] = tt < T;
+                rowok[ks] = (t0 + 4 * ks + lr) < T;
 #pragma unroll
-                for (int mt = 0; mt < KT; ++mt) {
-                    const int i = mt * 8 + lc;
-                    a[ks][mt] = (rowok[ks] && i < k) ? Lp[(long)i * sLi + (long)tt * sLt] : 0.0;
-                }
+                for (int mt = 0; mt < KT; ++mt) a[ks][mt] = a_next[ks][mt];
             }
+            if (rt + 1 < ntiles) load_left(rt + 1);
             mbar_wait(&pipe.full[s], ph);
             const double* tl = tiles + s * stage_doubles;
 #pragma unroll

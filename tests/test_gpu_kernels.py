@@ -249,13 +249,16 @@ def test_small_gram(k, n):
     close(o3.cpu().numpy(), pair, rtol=1e-12, atol=1e-11)
 
 
+@pytest.mark.parametrize('singular', [False, True])
 @pytest.mark.parametrize('k', [1, 2, 3, 8, 20, 64])
-def test_gpnh_solve_matrix_matches_lstsq(k):
+def test_gpnh_solve_matrix_matches_lstsq(k, singular):
+    """Cholesky fast path (regular Z'Z) and Jacobi pseudo-inverse (singular Z'Z: the
+    minimum-norm branch of numpy.linalg.lstsq) against lstsq itself."""
     rs = np.random.RandomState(k)
     T, d = 300, 57
     Z = orc.right_stochastic_matrix((T, k), rs)
-    if k > 3:
-        Z[:, 2] = 0.0                       # singular Z'Z: minimum-norm branch of lstsq
+    if singular and k > 3:
+        Z[:, 2] = 0.0
         Z /= Z.sum(axis=1)[:, None]
     ZtZ = Z.T.dot(Z)
     rhs = rs.standard_normal((k, 11))
@@ -268,6 +271,12 @@ def test_gpnh_solve_matrix_matches_lstsq(k):
         ref = np.linalg.lstsq(lhs, rhs / T, rcond=None)[0]
         got = P.cpu().numpy().dot(rhs)
         close(got, ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+    S = rs.standard_normal((k + 2, k))
+    S = S.T.dot(S)
+    P = be.zeros(k, k)
+    be.check(be.library().cdr_sym_pinv(be.to_device(S).data_ptr(), k, P.data_ptr(), None,
+                                       be.stream_ptr()), 'pinv')
+    close(P.cpu().numpy().dot(S), np.eye(k), rtol=0, atol=1e-8)
 
 
 # ---------------------------------------------------------------- furthest sum

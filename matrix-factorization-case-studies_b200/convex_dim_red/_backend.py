@@ -336,6 +336,12 @@ def graphs_disabled():
     return os.environ.get('CDR_NO_CUDA_GRAPH', '0') == '1'
 
 
+def graph_collectives():
+    """Whether NCCL collectives are captured into the iteration graph (``CDR_GRAPH_NCCL``,
+    default on; set to 0 to launch sharded iterations eagerly)."""
+    return os.environ.get('CDR_GRAPH_NCCL', '1') == '1'
+
+
 def capture_graph(fn):
     """Capture the kernels ``fn`` enqueues on the current stream into a CUDA graph.
 

@@ -48,7 +48,7 @@ def run_benchmark(args, X, Z0, F0, rank, world, sampler):
     n0 = lib.cdr_launch_count()
     eng.iteration()                                  # eager: first warm-up step
     launches_per_step = lib.cdr_launch_count() - n0
-    graph = None if (be.graphs_disabled() or world > 1) else be.capture_graph(eng.iteration)
+    graph = None if (be.graphs_disabled() or (world > 1 and not be.graph_collectives())) else be.capture_graph(eng.iteration)
     step = graph.replay if graph is not None else eng.iteration
     for _ in range(max(args.warmup - 1, 0)):
         step()

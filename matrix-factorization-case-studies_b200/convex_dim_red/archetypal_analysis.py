@@ -315,7 +315,7 @@ class _AaEngine:
         if use_graph is None:
             use_graph = not be.graphs_disabled()
         use_graph = (use_graph and self.graph_capturable() and not verbose and
-                     not self.comm.enabled)
+                     (not self.comm.enabled or be.graph_collectives()))
         be.trace('aa: engine ready')
         self.initial_cost()
         be.trace('aa: initial cost')

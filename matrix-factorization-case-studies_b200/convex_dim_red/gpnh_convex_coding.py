@@ -165,7 +165,7 @@ class _GpnhEngine:
     def run(self, verbose=0, use_graph=None):
         torch = be.torch_mod()
         if use_graph is None:
-            use_graph = not be.graphs_disabled() and not self.comm.enabled
+            use_graph = not be.graphs_disabled() and (not self.comm.enabled or be.graph_collectives())
         be.trace('gpnh: engine ready')
         self.initial_cost()
         be.trace('gpnh: initial cost')

@@ -189,14 +189,52 @@ def zeros(*shape, dtype=None):
     return torch.zeros(*shape, dtype=dtype or torch.float64, device='cuda')
 
 
-def to_device_padded(a, dtype=np.float64):
-    """Copy a 2-D host array into a zero-padded (rows, round_up(cols)) device buffer."""
+_RESIDENT = {}
+
+
+def _cache_key(a):
+    return (a.__array_interface__['data'][0], a.shape, a.strides, a.dtype.str)
+
+
+class DeviceCache:
+    """Keeps padded device copies of the given host arrays for the duration of a ``with``
+    block; ``to_device_padded`` returns the cached copy for the same memory.  The caller
+    promises not to modify the arrays (or the device copies) inside the block."""
+
+    def __init__(self, arrays):
+        self.arrays = [a for a in arrays if isinstance(a, np.ndarray) and a.ndim == 2]
+        self.keys = []
+
+    def __enter__(self):
+        for a in self.arrays:
+            if a.dtype == np.float64 and a.flags.c_contiguous:
+                key = _cache_key(a)
+                if key not in _RESIDENT:
+                    _RESIDENT[key] = _upload_padded(a)
+                    self.keys.append(key)
+        return self
+
+    def __exit__(self, *exc):
+        for key in self.keys:
+            _RESIDENT.pop(key, None)
+
+
+def _upload_padded(a):
     torch = require_cuda()
-    a = np.ascontiguousarray(a, dtype=dtype)
     rows, cols = a.shape
     buf = torch.zeros((rows, round_up(cols)), dtype=torch.float64, device='cuda')
     buf[:, :cols].copy_(torch.from_numpy(a))
     return buf
+
+
+def to_device_padded(a, dtype=np.float64):
+    """Copy a 2-D host array into a zero-padded (rows, round_up(cols)) device buffer."""
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if _RESIDENT:
+        hit = _RESIDENT.get(_cache_key(a))
+        if hit is not None:
+            return hit
+    return _upload_padded(a)
 
 
 def to_device(a, dtype=np.float64):

@@ -44,7 +44,7 @@ def kmeans_lloyd(X, init_centres, tol=1e-4, max_iter=300, verbose=False):
     if k > be.MAX_COMPONENTS:
         raise ValueError('n_clusters > %d is not supported by the B200 build' % be.MAX_COMPONENTS)
     s = be.stream_ptr
-    Xd = be.to_device_padded(X)
+    Xd = be._upload_padded(X)          # private copy: it is centred in place below
     ldx = Xd.stride(0)
     ldt = be.round_up(T)
 

@@ -333,3 +333,46 @@ def test_kmeans_furthest_sum_init(golden):
     km = KMeans(n_clusters=5, init=X[picks]).fit(X)
     assert np.array_equal(km.labels_, golden['km/conv/labels'])
     assert np.array_equal(km.predict(X), km.labels_)
+
+
+# ---------------------------------------------------------------- driver logic (restarts)
+def test_fit_models_keep_the_best_restart(golden):
+    from convex_dim_red import model_selection as ms
+    X = golden['aa/X']
+    train, val = ms.train_validation_split(X, 0.1)
+    assert train.shape[0] == int(np.ceil(0.9 * X.shape[0])) and train.shape[0] + val.shape[0] == X.shape[0]
+    best = ms.fit_aa_model(train, n_components=3, n_init=4, tolerance=1e-6, max_iterations=60,
+                           random_state=0)
+    # replay the restarts by hand from the same shared RNG (bin/run_hadisst_aa.py:154-172)
+    rng = np.random.RandomState(0)
+    costs = []
+    for _ in range(4):
+        m = cdr.ArchetypalAnalysis(n_components=3, init='random', tolerance=1e-6, max_iterations=60,
+                                   random_state=rng, dictionary_solver_kwargs=dict(max_iterations=1))
+        m.fit_transform(train)
+        costs.append(m.cost)
+    assert best.cost == min(costs)
+    res = ms.evaluate_model(best, train, val)
+    assert res['training_cost'] == best.cost
+    assert res['validation_cost'] > 0 and res['validation_rmse'] > 0 and res['training_rmse'] > 0
+    g = ms.fit_gpnh_model(train, n_components=3, lambda_W=0.1, n_init=3, max_iterations=40,
+                          random_state=1)
+    assert g.dictionary.shape == (X.shape[1], 3) and g.cost > 0
+    km = ms.fit_kmeans_model(golden['km/X'], n_components=5, init='furthest_sum', random_state=0)
+    assert km.labels_.shape == (golden['km/X'].shape[0],) and km.inertia_ > 0
+    folds = ms.time_series_cross_validate(ms.fit_gpnh_model, train, n_folds=3, n_components=2,
+                                          n_init=1, max_iterations=20, random_state=0)
+    assert len(folds) == 3 and all(f['test_cost'] > 0 for f in folds)
+
+
+def test_resident_cache_is_transparent(golden):
+    from convex_dim_red import model_selection as ms
+    from convex_dim_red import _backend as be
+    X = np.ascontiguousarray(golden['gpnh/X'])
+    W0, Z0 = golden['gpnh/W0'], golden['gpnh/Z0']
+    r1 = gp._iterate_gpnh_convex_coding(X, Z0.copy(), W0.copy(), tolerance=1e-9, max_iterations=5)
+    with ms.resident(X):
+        assert be.to_device_padded(X) is be.to_device_padded(X)
+        r2 = gp._iterate_gpnh_convex_coding(X, Z0.copy(), W0.copy(), tolerance=1e-9, max_iterations=5)
+    assert not be._RESIDENT
+    assert np.array_equal(r1[0], r2[0]) and r1[2] == r2[2]

@@ -1,0 +1,119 @@
+"""Full-size (BASELINE.json shape) checks through size-independent properties: the oracle
+cannot run at 1620 x 44 000 in seconds, so these verify invariants the domain offers --
+monotone cost, feasibility of the factors, agreement of the trace-form cost with the direct
+residual, linearity of the streaming passes and a checksum of checksums."""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip('torch')
+if not torch.cuda.is_available():          # pragma: no cover
+    pytest.skip('needs a CUDA device', allow_module_level=True)
+
+from convex_dim_red import _backend as be                                   # noqa: E402
+from convex_dim_red import archetypal_analysis as aa                        # noqa: E402
+from convex_dim_red import gpnh_convex_coding as gp                         # noqa: E402
+from convex_dim_red.datasets import synthetic_field                         # noqa: E402
+from convex_dim_red.stochastic_matrices import right_stochastic_matrix      # noqa: E402
+
+T, D, K = 1620, 44000, 8
+
+
+@pytest.fixture(scope='module')
+def hadisst():
+    return synthetic_field(T, D, seed=0)
+
+
+def test_gpnh_full_size_invariants(hadisst):
+    X = hadisst
+    rs = np.random.RandomState(0)
+    W0 = np.sqrt(np.abs(X).mean() / K) * rs.randn(D, K)
+    Z0 = right_stochastic_matrix((T, K), random_state=rs)
+    Z, W, cost, n_iter, _, deltas = gp._iterate_gpnh_convex_coding(
+        X, Z0, W0, lambda_W=0.05, tolerance=0.0, max_iterations=6)
+    assert n_iter == 5 and len(deltas) == 6
+    assert all(d <= 1e-9 for d in deltas)                       # monotone decrease
+    assert np.all(Z >= 0) and np.allclose(Z.sum(axis=1), 1, 1e-12)
+    assert W.shape == (D, K)
+    # the loop's trace-form cost equals the direct residual cost (gpnh_convex_coding.py:199-210)
+    direct = gp._gpnh_cost(X, Z, W, lambda_W=0.05)
+    np.testing.assert_allclose(cost, direct, rtol=1e-9)
+    # the dictionary is the least-squares solution for the final... previous weights: one more
+    # dictionary step cannot increase the cost
+    W2 = gp._update_gpnh_dictionary(X, Z, Z.T.dot(Z), 4.0 / (D * K * (K - 1)) * (K * np.eye(K) - 1),
+                                    lambda_W=0.05)
+    assert gp._gpnh_cost(X, Z, W2, lambda_W=0.05) <= direct * (1 + 1e-12)
+
+
+def test_aa_full_size_invariants(hadisst):
+    X = hadisst
+    rs = np.random.RandomState(1)
+    C0 = right_stochastic_matrix((K, T), random_state=rs)
+    Z0 = right_stochastic_matrix((T, K), random_state=rs)
+    Z, C, alpha, cost, n_iter, _, deltas = aa._iterate_aa(
+        X, Z0, C0, np.ones(K), tolerance=0.0, max_iterations=5,
+        dictionary_solver_kwargs=dict(max_iterations=1))
+    assert n_iter == 4
+    assert all(d <= 1e-9 for d in deltas)
+    assert np.all(Z >= 0) and np.allclose(Z.sum(axis=1), 1, 1e-12)
+    assert np.all(C >= 0) and np.allclose(C.sum(axis=1), 1, 1e-12)
+    # cost = 1/2 ||X - Z C X||^2 / T, evaluated directly with the residual kernel
+    archetypes = C.dot(X)
+    direct = gp._gpnh_cost(X, Z, archetypes.T, lambda_W=0)
+    np.testing.assert_allclose(cost, direct, rtol=1e-8)
+
+
+def test_streaming_passes_linearity_and_checksum(hadisst):
+    X = hadisst
+    rs = np.random.RandomState(2)
+    Xd = be.to_device_padded(X)
+    ws = be.Workspace(T, D, K)
+    L1, L2 = rs.standard_normal((K, T)), rs.standard_normal((K, T))
+    outs = []
+    for L in (L1, L2, L1 + 2.0 * L2):
+        Ld = be.to_device_padded(L)
+        o = be.zeros(K, Xd.stride(0))
+        be.reduce_samples(Ld, Ld.stride(0), 1, Xd, T, D, K, o, ws)
+        outs.append(be.to_host(o, K, D))
+    scale = np.abs(outs[2]).max()
+    np.testing.assert_allclose(outs[2], outs[0] + 2.0 * outs[1], rtol=0, atol=1e-12 * scale)
+    # checksum of checksums with random weights u (the columns of X have zero mean, so plain
+    # sums would only compare rounding noise): sum_f u_f (L X)[j, f] = L[j, :] . (X u)
+    u = rs.standard_normal(D)
+    np.testing.assert_allclose(outs[0].dot(u), L1.dot(X.dot(u)), rtol=1e-9)
+
+    M1, M2 = rs.standard_normal((K, D)), rs.standard_normal((K, D))
+    fouts = []
+    for M in (M1, M2, M1 - 0.5 * M2):
+        Md = be.to_device_padded(M)
+        o = be.zeros(K, be.round_up(T))
+        be.reduce_features(Md, Xd, T, D, K, o, ws)
+        fouts.append(be.to_host(o, K, T))
+    scale = np.abs(fouts[2]).max()
+    np.testing.assert_allclose(fouts[2], fouts[0] - 0.5 * fouts[1], rtol=0, atol=1e-12 * scale)
+    v = rs.standard_normal(T)
+    np.testing.assert_allclose(fouts[0].dot(v), M1.dot(v.dot(X)), rtol=1e-9)
+    # spot rows against NumPy
+    idx = [0, 1, 811, T - 1]
+    np.testing.assert_allclose(fouts[0][:, idx], M1.dot(X[idx].T), rtol=1e-11, atol=1e-9)
+    cols = [0, 7, 21999, D - 1]
+    np.testing.assert_allclose(outs[0][:, cols], L1.dot(X[:, cols]), rtol=1e-11, atol=1e-9)
+
+
+def test_weights_update_idempotent_at_full_batch(hadisst):
+    """Re-solving the per-sample QPs from their own solution leaves it unchanged to solver
+    accuracy (idempotence), T = 18 000 samples, k = 8."""
+    rs = np.random.RandomState(3)
+    n, k = 18000, 8
+    Mx = rs.standard_normal((k + 3, k))
+    A = Mx.T.dot(Mx)
+    B = rs.standard_normal((k, n)) * 3.0
+    Z0 = right_stochastic_matrix((n, k), random_state=rs)
+    Z1 = aa._update_kernel_aa_weights(Z0, np.ones(k), B, A)
+    Z2 = aa._update_kernel_aa_weights(Z1, np.ones(k), B, A)
+    assert np.all(Z1 >= 0) and np.allclose(Z1.sum(axis=1), 1, 1e-12)
+    np.testing.assert_allclose(Z2, Z1, rtol=0, atol=5e-6)
+    obj = lambda Zm: 0.5 * np.einsum('ti,ij,tj->t', Zm, A, Zm) - np.einsum('ti,it->t', Zm, B)
+    assert np.all(obj(Z1) <= obj(Z0) + 1e-12)

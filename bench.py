@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument('--rows', type=int, default=T_ROWS)
     ap.add_argument('--features', type=int, default=N_FEATURES)
     ap.add_argument('--components', type=int, default=N_COMPONENTS)
+    ap.add_argument('--formulation', choices=('stream', 'gram'), default='stream',
+                    help="AA only: 'gram' builds K = X X' once and iterates on K (opt-in "
+                         "algorithmic variant; the headline numbers use 'stream')")
     ap.add_argument('--cpu-steps', type=int, default=4,
                     help='outer iterations of the CPU baseline sample (0 disables it)')
     return ap.parse_args()
@@ -202,7 +205,10 @@ def config_dict(args, world):
                            1 if args.workload == 'gpnh' else 0),
             'n_samples_total': args.rows * world, 'n_features': args.features,
             'n_components': args.components, 'lambda_W': LAMBDA_W,
-            'formulation': 'streaming (X read from HBM every pass; 2 passes/iter GPNH, 4 AA)',
+            'formulation': ('streaming (X read from HBM every pass; 2 passes/iter GPNH, 4 AA)'
+                            if args.formulation == 'stream' else
+                            'gram (K = X X^T built once, 2 passes over the L2-resident K per '
+                            'iteration; no HBM roofline applies)'),
             'l2_policy': 'X (570 MB per GPU) is larger than the 126 MB L2; no explicit flush',
             'sharding': 'sample axis, %d rank(s)' % world}
 
@@ -224,8 +230,15 @@ def run_b200(args):
     if rank == 0:
         peak, peak_src = peaks()
         roof = result['roofline']
-        roof.update({'bound': 'hbm', 'peak': peak, 'unit': 'GB/s', 'frac': roof['achieved'] / peak,
-                     'peak_source': peak_src})
+        if roof is not None:
+            roof.update({'bound': 'hbm', 'peak': peak, 'unit': 'GB/s',
+                         'frac': roof['achieved'] / peak, 'peak_source': peak_src})
+            tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+            if os.path.exists(tpath):
+                with open(tpath) as fh:
+                    tr = json.load(fh)
+                roof['traffic'] = tr['dram_bytes_per_launch'].get(roof['kernel'])
+                roof['traffic_source'] = tr['source']
         line = {
             'metric': metric_name(args), 'value': result['value'], 'unit': 'iterations/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -234,6 +247,7 @@ def run_b200(args):
             'config': config_dict(args, world), 'clocks': result['clocks'],
             'e2e': result['e2e'], 'gpu_launches': result['gpu_launches'],
             'roofline': roof, 'kernels': result['kernels'], 'final_cost': result['final_cost'],
+            'time_to_converge': result['time_to_converge'],
         }
         if args.cpu_steps > 0 and world == 1:
             times, cost = cpu_steps(args, X, Z0, F0, args.cpu_steps)
@@ -243,6 +257,10 @@ def run_b200(args):
                 'sample': 'first %d outer iterations of the same workload from the same start '
                           '(oracle port of the reference loop)' % args.cpu_steps,
                 'final_cost': cost}
+            ttc = line.get('time_to_converge')
+            if ttc:
+                # not run: iterations of the converged CUDA fit x the CPU time per iteration
+                ttc['cpu_estimate_seconds'] = ttc['iterations'] * sum(times) / args.cpu_steps
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -15,6 +15,14 @@ def _make_engine(args, X, Z0, F0, Xd=None, comm=None):
     if args.workload == 'gpnh':
         return _GpnhEngine(X, Z0, F0, lambda_W=0.0, tolerance=0.0, max_iterations=big,
                            require_monotonic_cost_decrease=False, X_device=Xd, comm=comm)
+    if getattr(args, 'formulation', 'stream') == 'gram':
+        from .archetypal_analysis import _ShapeOnly
+        T, d = X.shape
+        trace = float(be.frobenius_sq(Xd, T, d).item())
+        return _AaEngine(_ShapeOnly((T, T)), Z0, F0, np.ones(F0.shape[0]), 'kernel', tolerance=0.0,
+                         max_iterations=big, require_monotonic_cost_decrease=False,
+                         dictionary_solver_kwargs=dict(max_iterations=1),
+                         data_device=be.gram(Xd, T, d), trace_data=trace, grad_scale=1.0 / T)
     return _AaEngine(X, Z0, F0, np.ones(F0.shape[0]), 'feature', tolerance=0.0,
                      max_iterations=big, require_monotonic_cost_decrease=False,
                      dictionary_solver_kwargs=dict(max_iterations=1), data_device=Xd, comm=comm)
@@ -79,7 +87,13 @@ def run_benchmark(args, X, Z0, F0, rank, world, sampler):
 
     # ---- the streaming passes on their own (roofline of the dominant kernel)
     ws = eng.ws
-    if args.workload == 'gpnh':
+    gram_mode = args.workload == 'aa' and getattr(args, 'formulation', 'stream') == 'gram'
+    if gram_mode:
+        t_gram = _time_launches(lambda: be.gram(Xd, T, d), reps=3)
+        roofline = None
+        kernels = {'gram_build_ms': t_gram, 'gram_build_tflops': 2.0 * T * T * d / (t_gram * 1e-3) / 1e12,
+                   'step_ms': ms / args.steps}
+    elif args.workload == 'gpnh':
         t_samples = _time_launches(lambda: be.reduce_samples(
             eng.Z, 1, k, eng.X, T, d, k, eng.WT, ws, E=eng.P))
         t_features = _time_launches(lambda: be.reduce_features(eng.WT, eng.X, T, d, k, eng.XWt, ws))
@@ -96,11 +110,13 @@ def run_benchmark(args, X, Z0, F0, rank, world, sampler):
             eng.CKCt, eng.alpha, eng.CK, 1, eng.ldt, eng.Z, T, k, eng.w_params)), reps=5)
         passes = 4
     pass_bytes = 8.0 * T * d
-    slow, name = max((t_samples, 'reduce_samples_kernel'), (t_features, 'reduce_features_kernel'))
-    roofline = {'kernel': name, 'achieved': pass_bytes / (slow * 1e-3) / 1e9,
-                'algorithmic_bytes_per_launch': pass_bytes, 'ms_per_launch': slow,
-                'traffic': None}
-    kernels = {'reduce_samples_ms': t_samples, 'reduce_features_ms': t_features,
+    if not gram_mode:
+        slow, name = max((t_samples, 'reduce_samples_tma_kernel'),
+                         (t_features, 'reduce_features_strip_kernel'))
+        roofline = {'kernel': name, 'achieved': pass_bytes / (slow * 1e-3) / 1e9,
+                    'algorithmic_bytes_per_launch': pass_bytes, 'ms_per_launch': slow,
+                    'traffic': None}
+    kernels = kernels if gram_mode else {'reduce_samples_ms': t_samples, 'reduce_features_ms': t_features,
                'reduce_samples_gbs': pass_bytes / (t_samples * 1e-3) / 1e9,
                'reduce_features_gbs': pass_bytes / (t_features * 1e-3) / 1e9,
                'qp_batched_ms': t_qp, 'passes_per_step': passes,
@@ -110,10 +126,12 @@ def run_benchmark(args, X, Z0, F0, rank, world, sampler):
 
     # ---- end to end through the public NumPy API (host buffers, pinned)
     e2e = run_e2e(args, X, Z0, F0, world, comm)
+    converge = run_to_convergence(args, X, Z0, F0, comm) if world == 1 else None
 
     return {'value': world * args.steps / (ms * 1e-3), 'ms_per_step': ms / args.steps,
             'clocks': sampler.summary(), 'gpu_launches': int(launches_per_step * args.steps),
-            'roofline': roofline, 'kernels': kernels, 'e2e': e2e, 'final_cost': st.cost}
+            'roofline': roofline, 'kernels': kernels, 'e2e': e2e, 'final_cost': st.cost,
+            'time_to_converge': converge}
 
 
 def run_e2e(args, X, Z0, F0, world, comm=None):
@@ -158,3 +176,27 @@ def run_e2e(args, X, Z0, F0, world, comm=None):
                     'X uploaded once from pinned host memory, factors read back'
                     % ('gpnh_convex_coding' if args.workload == 'gpnh' else 'aa', K),
             'seconds': elapsed}
+
+
+def run_to_convergence(args, X, Z0, F0, comm=None, tolerance=1e-4, max_iterations=10000):
+    """Wall time of one public-API fit to the drivers' stopping rule (abs_delta_f, tolerance
+    1e-4 as in bin/run_hadisst_aa_wrapper.sh:44, max_iterations 10 000), host buffers in,
+    factors out."""
+    torch = be.torch_mod()
+    from . import archetypal_analysis as aa
+    from . import gpnh_convex_coding as gp
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    if args.workload == 'gpnh':
+        out = gp._iterate_gpnh_convex_coding(X, Z0, F0, lambda_W=0.0, tolerance=tolerance,
+                                             max_iterations=max_iterations, comm=comm)
+        cost, n_iter = out[2], out[3]
+    else:
+        out = aa._iterate_aa(X, Z0, F0, np.ones(F0.shape[0]), tolerance=tolerance,
+                             max_iterations=max_iterations,
+                             dictionary_solver_kwargs=dict(max_iterations=1), comm=comm,
+                             formulation=getattr(args, 'formulation', 'stream'))
+        cost, n_iter = out[3], out[4]
+    torch.cuda.synchronize()
+    return {'seconds': time.perf_counter() - t0, 'iterations': int(n_iter) + 1,
+            'tolerance': tolerance, 'stopping_criterion': 'abs_delta_f', 'cost': float(cost)}

@@ -68,7 +68,7 @@ class _AaEngine:
                  require_monotonic_cost_decrease=True, weights_solver_kwargs=None,
                  dictionary_solver_kwargs=None, scale_factors_solver_kwargs=None,
                  update_weights=True, update_dictionary=True, update_scale_factors=True,
-                 trace_data=None, data_device=None, comm=None):
+                 trace_data=None, data_device=None, comm=None, grad_scale=None):
         torch = be.require_cuda()
         self.mode = mode
         # sample-sharded fit: `data` / `weights` hold this rank's rows; the dictionary and
@@ -138,7 +138,8 @@ class _AaEngine:
         self.state.write_field('trace_data', self.trace_data)
         # archetypal_analysis.py:265,277 divide the dictionary cost by k; the gradient is
         # divided by T in feature space (:297) and by k in kernel space (:288)
-        grad_scale = 1.0 / T if mode == 'feature' else 1.0 / k
+        if grad_scale is None:
+            grad_scale = 1.0 / T if mode == 'feature' else 1.0 / k
         self.buf = be.AaBuffers(
             self.C.data_ptr(), self.G.data_ptr(), self.D.data_ptr(), self.CK.data_ptr(),
             self.DK.data_ptr(), self.KZt.data_ptr(), self.alpha.data_ptr(),
@@ -592,12 +593,41 @@ def _update_kernel_aa_weights(weights, alpha, CK, CKCt, **solver_kwargs):
     return _solve_weights(CKCt, alpha, CK, weights, be.make_spg_params(solver_kwargs))
 
 
+class _ShapeOnly:
+    """Stand-in for a host matrix that only lives on the device."""
+
+    def __init__(self, shape):
+        self.shape = tuple(shape)
+
+
 def _iterate(data, weights, dictionary, alpha, mode, delta, update_weights,
              update_dictionary, update_scale_factors, tolerance, max_iterations, verbose,
              kwargs):
     be.trace('aa: enter _iterate')
-    eng = _engine(
-        data, weights, dictionary, alpha, mode, delta=delta, tolerance=tolerance,
+    grad_scale = None
+    if mode == 'feature' and kwargs.get('formulation', 'stream') == 'gram':
+        # Opt-in Gram-space formulation of the *feature-space* problem: K = X X' is built once
+        # on the device (T x T, L2-resident at HadISST shape) and every later product is a pass
+        # over K instead of two passes over X.  Same cost / gradient scaling as _iterate_aa
+        # (gradient / T); only the rounding of (C X) X' vs C (X X') differs.
+        if kwargs.get('comm') is not None and kwargs['comm'].enabled:
+            raise NotImplementedError("formulation='gram' is single-GPU")
+        data = np.asarray(data, dtype=np.float64)
+        T, d = data.shape
+        Xd = kwargs.get('data_device')
+        if Xd is None:
+            Xd = be.to_device_padded(data)
+        trace = kwargs.get('trace_data')
+        if trace is None:
+            trace = float(be.frobenius_sq(Xd, T, d).item())
+        kwargs = dict(kwargs, data_device=be.gram(Xd, T, d), trace_data=trace)
+        data, mode, grad_scale = _ShapeOnly((T, T)), 'kernel', 1.0 / T
+    elif kwargs.get('formulation', 'stream') not in ('stream', 'gram'):
+        raise ValueError("formulation must be 'stream' or 'gram'")
+    eng = _AaEngine(
+        data if isinstance(data, _ShapeOnly) else np.asarray(data, dtype=np.float64),
+        np.asarray(weights, dtype=np.float64), np.asarray(dictionary, dtype=np.float64), alpha,
+        mode, grad_scale=grad_scale, delta=delta, tolerance=tolerance,
         max_iterations=max_iterations,
         stopping_criterion=kwargs.get('stopping_criterion', 'abs_delta_f'),
         require_monotonic_cost_decrease=kwargs.get('require_monotonic_cost_decrease', True),
@@ -660,6 +690,9 @@ class _AaBase():
         self.require_monotonic_cost_decrease = kwargs.get(
             'require_monotonic_cost_decrease', True)
         self.stopping_criterion = kwargs.get('stopping_criterion', 'abs_delta_f')
+        # 'stream' (default: products with X, as the reference) or 'gram' (ArchetypalAnalysis
+        # only: one Gram matrix up front, then passes over K)
+        self.formulation = kwargs.get('formulation', 'stream')
         self.weights = None
         self.dictionary = None
         self.alpha = None
@@ -792,7 +825,7 @@ class ArchetypalAnalysis(_AaBase):
                               update_dictionary, update_weights, kwargs)
         del kernel
         return self._run(_iterate_aa, data64, update_weights, update_dictionary,
-                         update_scale_factors, data_device=Xd)
+                         update_scale_factors, data_device=Xd, formulation=self.formulation)
 
     def fit_transform(self, data, dictionary=None, weights=None, alpha=None, **kwargs):
         """Perform archetypal analysis and return transformed data

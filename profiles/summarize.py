@@ -45,6 +45,23 @@ def kernels(rep, out):
     raw = subprocess.check_output(['ncu', '-i', rep, '--page', 'raw', '--csv']).decode()
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
+    # DRAM traffic per launch (read + write) of each kernel -> profiles/ncu_traffic.json,
+    # which bench.py reports as roofline.traffic
+    import json
+    traffic = {}
+    for row in rows[2:]:
+        name = re.sub(r'\(.*', '', row[hdr.index('Kernel Name')]).replace('void ', '').split('<')[0]
+        tot = 0.0
+        for m in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            i = hdr.index(m)
+            v = float(row[i].replace(',', ''))
+            scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[units[i]]
+            tot += v * scale
+        traffic.setdefault(name, []).append(tot)
+    with open('profiles/ncu_traffic.json', 'w') as fh:
+        json.dump({'source': rep + ' (ncu --set full, per launch, read + write)',
+                   'dram_bytes_per_launch': {k: sum(v) / len(v) for k, v in traffic.items()}}, fh,
+                  indent=1)
     with open(out, 'w') as fh:
         fh.write('# ncu --set full --clock-control none --import-source on (one capture per kernel)\n')
         for row in rows[2:]:

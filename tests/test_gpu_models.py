@@ -376,3 +376,24 @@ def test_resident_cache_is_transparent(golden):
         r2 = gp._iterate_gpnh_convex_coding(X, Z0.copy(), W0.copy(), tolerance=1e-9, max_iterations=5)
     assert not be._RESIDENT
     assert np.array_equal(r1[0], r2[0]) and r1[2] == r2[2]
+
+
+def test_aa_gram_formulation_matches_streaming(golden):
+    """formulation='gram' (K = X X' once, then passes over K) follows the same trajectory as
+    the default streaming formulation up to rounding."""
+    X, K, C0, Z0, alpha = _aa_inputs(golden)
+    kw = dict(tolerance=1e-9, max_iterations=12, dictionary_solver_kwargs=dict(max_iterations=1))
+    a = aa._iterate_aa(X, Z0.copy(), C0.copy(), alpha.copy(), **kw)
+    b = aa._iterate_aa(X, Z0.copy(), C0.copy(), alpha.copy(), formulation='gram', **kw)
+    assert a[4] == b[4]
+    close(b[3], a[3], rtol=1e-8)
+    close(b[0], a[0], rtol=0, atol=2e-5)
+    close(b[1], a[1], rtol=0, atol=2e-5)
+    close(b[3], golden['aa/faa_d1/stats'][0], rtol=1e-7)
+    m = cdr.ArchetypalAnalysis(n_components=4, init='random', tolerance=1e-6, max_iterations=40,
+                               random_state=0, dictionary_solver_kwargs=dict(max_iterations=1),
+                               formulation='gram')
+    m.fit_transform(X)
+    close(m.cost, golden['aa/est_random/stats'][0], rtol=1e-6)
+    with pytest.raises(ValueError):
+        aa._iterate_aa(X, Z0.copy(), C0.copy(), alpha.copy(), formulation='nope', **kw)

@@ -221,6 +221,9 @@ def run_b200(args):
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # the exchanged payloads are small (k x d = 2.8 MB, k x k): the low-latency protocol
+        # measured 40 us vs 52 us for the 2.8 MB all-reduce on 8 GPUs (profiles/bench_allreduce.py)
+        os.environ.setdefault('NCCL_PROTO', 'LL')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     from convex_dim_red import _backend as be
     from convex_dim_red import _bench_support as bs

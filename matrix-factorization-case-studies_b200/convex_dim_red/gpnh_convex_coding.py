@@ -67,10 +67,13 @@ class _GpnhEngine:
         self.Z = be.to_device(weights)
         self.WT = be.to_device_padded(np.ascontiguousarray(np.asarray(dictionary).T))
         self.XWt = be.zeros(k, self.ldt)
-        # the two statistics that reduce over samples share one buffer (one all-reduce)
-        self.stats = be.zeros(2, k, k)
+        # the statistics that reduce over samples share one buffer (one all-reduce):
+        # Z'Z, (X W)'Z and -- sharded fits only -- the (X W)'Z of the dictionary sub-step
+        self.stats = be.zeros(3, k, k)
         self.ZtZ = self.stats[0]
         self.XWtZ = self.stats[1]
+        self.XWtZ_dict = self.stats[2]
+        self.ZtZ_prev = be.zeros(k, k)
         self.WtW = be.zeros(k, k)
         self.REG = be.zeros(k, k)
         self.P = be.zeros(k, k)
@@ -106,10 +109,12 @@ class _GpnhEngine:
         k, d = self.k, self.d
         return (self.WT, self.ldx, 1, k, self.WT, self.ldx, 1, k, d, self.REG, 1.0, 1)
 
-    def _cost_check(self, stage, end, with_reg):
+    def _cost_check(self, stage, end, with_reg, XWtZ=None, ZtZ=None):
+        XWtZ = self.XWtZ if XWtZ is None else XWtZ
+        ZtZ = self.ZtZ if ZtZ is None else ZtZ
         be.check(self.lib.cdr_gpnh_cost_check(
-            self.state.ptr, self.state.cost_deltas.data_ptr(), self.XWtZ.data_ptr(),
-            self.ZtZ.data_ptr(), self.WtW.data_ptr(),
+            self.state.ptr, self.state.cost_deltas.data_ptr(), XWtZ.data_ptr(),
+            ZtZ.data_ptr(), self.WtW.data_ptr(),
             self.REG.data_ptr() if with_reg else None, self.k, self.T_total, self.d,
             self.lambda_W, stage, int(end), be.stream_ptr()), 'cdr_gpnh_cost_check')
 
@@ -122,7 +127,7 @@ class _GpnhEngine:
         if self.lambda_W != 0:
             descs.append(self._desc_REG())
         be.small_gram(descs, self.ws, flags)
-        self.comm.allreduce_sum(self.stats)
+        self.comm.allreduce_sum(self.stats[:2])
         self._cost_check(0, False, self.lambda_W != 0)
 
     def dictionary_step(self, stage=2, end=False, flags=True):
@@ -140,9 +145,19 @@ class _GpnhEngine:
         if self.lambda_W != 0:
             descs.append(self._desc_REG())
         be.small_gram(descs, self.ws, fl)
+        if self._defer_dictionary_check(stage, end):
+            # sharded full iteration: the k x k all-reduce latency (~30 us on 8 GPUs) is paid
+            # once per iteration -- this sub-step's (X W)'Z partial rides along with the
+            # statistics of the weights sub-step and both cost checks run after it
+            self.XWtZ_dict.copy_(self.XWtZ)
+            self.ZtZ_prev.copy_(self.ZtZ)
+            return
         self.comm.allreduce_sum(self.XWtZ)
         if stage is not None:
             self._cost_check(stage, end, self.lambda_W != 0)
+
+    def _defer_dictionary_check(self, stage, end):
+        return self.comm.enabled and stage == 2 and not end and self.update_weights
 
     def weights_step(self, stage=3, end=True, flags=True):
         """gpnh_convex_coding.py:371-384."""
@@ -150,7 +165,13 @@ class _GpnhEngine:
         be.quad_simplex_spg_batched(self.WtW, None, self.XWt, 1, self.ldt, self.Z, self.T,
                                     self.k, self.params, flags=fl)
         be.small_gram([self._desc_ZtZ(), self._desc_XWtZ()], self.ws, fl)
-        self.comm.allreduce_sum(self.stats)
+        if self.comm.enabled and self.update_dictionary and stage == 3:
+            self.comm.allreduce_sum(self.stats)
+            # deferred check of the dictionary sub-step (its own (X W)'Z, the old Z'Z) ...
+            self._cost_check(2, False, self.lambda_W != 0, XWtZ=self.XWtZ_dict,
+                             ZtZ=self.ZtZ_prev)
+        else:
+            self.comm.allreduce_sum(self.stats[:2])
         if stage is not None:
             self._cost_check(stage, end, False)
 

@@ -58,6 +58,10 @@ def run_benchmark(args, X, Z0, F0, rank, world, sampler):
     launches_per_step = lib.cdr_launch_count() - n0
     graph = None if (be.graphs_disabled() or (world > 1 and not be.graph_collectives())) else be.capture_graph(eng.iteration)
     step = graph.replay if graph is not None else eng.iteration
+    # clocks / throttle reasons are sampled from the warm-up through the timed region and the
+    # per-kernel timings (the timed region alone lasts a few milliseconds, shorter than one
+    # nvidia-smi query)
+    sampler.__enter__()
     for _ in range(max(args.warmup - 1, 0)):
         step()
     torch.cuda.synchronize()
@@ -65,13 +69,12 @@ def run_benchmark(args, X, Z0, F0, rank, world, sampler):
         dist.barrier()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
-    with sampler:
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(args.steps):
-            step()
-        e1.record()
-        torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device='cuda')
@@ -123,6 +126,13 @@ def run_benchmark(args, X, Z0, F0, rank, world, sampler):
                'step_ms': ms / args.steps,
                'streaming_share_of_step': passes / 2.0 * (t_samples + t_features) /
                (ms / args.steps)}
+
+    # keep the GPU busy with 1000 more steps (a fixed count: every rank must issue the same
+    # collectives) so that several clock samples land under load, then stop sampling
+    for _ in range(1000):
+        step()
+    torch.cuda.synchronize()
+    sampler.__exit__(None, None, None)
 
     # ---- end to end through the public NumPy API (host buffers, pinned)
     e2e = run_e2e(args, X, Z0, F0, world, comm)

@@ -502,7 +502,15 @@ extern "C" int cdr_reduce_features(const double* M, long ldm, const double* X, l
 
 extern "C" size_t cdr_gram_workspace_bytes(int T, int d)
 {
-    return cdr_reduce_features_workspace_bytes(T, d, 64);
+    // 64-row slabs use the direct-load kernel; a short last slab (<= 16 rows) may take the
+    // strip-owned kernel, whose partials are sized differently
+    size_t need = cdr_reduce_features_workspace_bytes(T, d, 64);
+    const int tail = T % 64;
+    if (tail != 0) {
+        const size_t t = cdr_reduce_features_workspace_bytes(T, d, tail);
+        if (t > need) need = t;
+    }
+    return need;
 }
 
 // First version: the Gram matrix as ceil(T/64) feature-reductions with M = a

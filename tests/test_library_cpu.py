@@ -152,3 +152,31 @@ def test_solver_option_defaults():
     assert (p.max_iterations, p.max_feval) == (1, 1000000)
     with pytest.raises(ValueError):
         be.make_spg_params({'memory': 99})
+
+
+def test_workspace_size_queries_are_consistent(lib):
+    """Host-only size queries: the Gram workspace must cover every slab the Gram routine
+    hands to the feature reduction (64-row slabs and the short last slab)."""
+    for T, d in ((18000, 44000), (1620, 44000), (700, 41800), (50, 33), (1000, 100000), (65, 5000)):
+        need = lib.cdr_gram_workspace_bytes(T, d)
+        assert need >= lib.cdr_reduce_features_workspace_bytes(T, d, 64)
+        if T % 64:
+            assert need >= lib.cdr_reduce_features_workspace_bytes(T, d, T % 64)
+        for k in (1, 8, 9, 16, 17, 64):
+            assert lib.cdr_reduce_samples_workspace_bytes(T, d, k) >= 0
+            assert lib.cdr_reduce_features_workspace_bytes(T, d, k) > 0
+    assert lib.cdr_small_gram_workspace_bytes() >= 4 * 64 * 64 * 8
+    assert lib.cdr_furthest_sum_workspace_bytes(1620, 8, 10) >= 1620 * 8 * (1 + 17)
+    assert lib.cdr_launch_count() == 0 or lib.cdr_launch_count() > 0
+
+
+def test_model_selection_host_helpers():
+    from convex_dim_red import model_selection as ms
+    X = np.arange(40, dtype=float).reshape(20, 2)
+    train, val = ms.train_validation_split(X, 0.1)
+    assert train.shape == (18, 2) and val.shape == (2, 2)          # ceil(0.9 * 20) = 18
+    a = np.array([[1.0, 2.0], [3.0, 6.0]])
+    b = np.array([[1.0, 0.0], [1.0, 2.0]])
+    # per-column RMSE, uniformly averaged: sqrt((0 + 4) / 2), sqrt((4 + 16) / 2)
+    np.testing.assert_allclose(ms.root_mean_squared_error(a, b),
+                               0.5 * (np.sqrt(2.0) + np.sqrt(10.0)))

@@ -135,14 +135,90 @@ def kmeans_lloyd(X, init_centres, tol=1e-4, max_iter=300, verbose=False):
     return (labels.cpu().numpy(), be.to_host(centres, k, d), inertia, n_iter)
 
 
+def _row_sqnorms_and_device(X):
+    """Device copy of X and its squared row norms (sklearn row_norms(X, squared=True))."""
+    lib = be.library()
+    T, d = X.shape
+    Xd = be.to_device_padded(X)
+    norms = be.zeros(T)
+    be.check(lib.cdr_row_sqnorms(Xd.data_ptr(), Xd.stride(0), T, d, norms.data_ptr(),
+                                 be.stream_ptr()), 'cdr_row_sqnorms')
+    return Xd, norms.cpu().numpy()
+
+
+def kmeans_plusplus(X, n_clusters, random_state=None, n_local_trials=None):
+    """k-means++ seeding, restating ``sklearn.cluster.kmeans_plusplus`` /
+    ``_kmeans_plusplus`` (scikit-learn 1.9.0 ``_kmeans.py:180-282``): same RNG calls in the
+    same order, same candidate selection.  The inner products candidates . samples are the
+    reduce-over-features pass; the O(n_samples) bookkeeping (potentials, cumulative sums,
+    ``searchsorted``) is host logic on vectors.  Returns ``(centers, indices)``.
+    """
+    rng = check_random_state(random_state)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    T, d = X.shape
+    if n_local_trials is None:
+        n_local_trials = 2 + int(np.log(n_clusters))
+    Xd, x_sq = _row_sqnorms_and_device(X)
+    ws = be.Workspace(T, d, max(1, min(n_local_trials, be.MAX_COMPONENTS)))
+    ldt = be.round_up(T)
+    sample_weight = np.ones(T)
+
+    def sq_distances(ids):
+        """_euclidean_distances(X[ids], X, squared=True): (-2 x.y + |x|^2) + |y|^2, clipped."""
+        ids = np.asarray(ids)
+        M = be.to_device_padded(X[ids])
+        dots = be.zeros(len(ids), ldt)
+        be.reduce_features(M, Xd, T, d, len(ids), dots, ws)
+        dist = -2.0 * be.to_host(dots, len(ids), T)
+        dist += x_sq[ids][:, np.newaxis]
+        dist += x_sq[np.newaxis, :]
+        np.maximum(dist, 0, out=dist)
+        return dist
+
+    centers = np.empty((n_clusters, d))
+    indices = np.full(n_clusters, -1, dtype=int)
+    center_id = rng.choice(T, p=sample_weight / sample_weight.sum())
+    centers[0] = X[center_id]
+    indices[0] = center_id
+    closest = sq_distances([center_id])
+    current_pot = closest @ sample_weight
+    for c in range(1, n_clusters):
+        rand_vals = rng.uniform(size=n_local_trials) * current_pot
+        candidate_ids = np.searchsorted(np.cumsum(sample_weight * closest, dtype=np.float64),
+                                        rand_vals)
+        np.clip(candidate_ids, None, closest.size - 1, out=candidate_ids)
+        dist = sq_distances(candidate_ids)
+        np.minimum(closest, dist, out=dist)
+        candidates_pot = dist @ sample_weight.reshape(-1, 1)
+        best = np.argmin(candidates_pot)
+        current_pot = candidates_pot[best]
+        closest = dist[best][np.newaxis, :]
+        best_id = candidate_ids[best]
+        centers[c] = X[best_id]
+        indices[c] = best_id
+    return centers, indices
+
+
+def _is_same_clustering(labels1, labels2, n_clusters):
+    """Same partition up to a relabelling (sklearn ``_is_same_clustering``)."""
+    mapping = np.full(n_clusters, -1, dtype=np.int64)
+    for a, b in zip(labels1, labels2):
+        if mapping[a] == -1:
+            mapping[a] = b
+        elif mapping[a] != b:
+            return False
+    return True
+
+
 class KMeans():
     """Minimal estimator around :func:`kmeans_lloyd` with the scikit-learn attribute
     names the reference's drivers read (``cluster_centers_``, ``labels_``, ``inertia_``,
     ``n_iter_``; bin/run_hadisst_kmeans.py:128-137).
 
-    ``init`` is an explicit (n_clusters, n_features) array, ``'furthest_sum'`` (start
-    index drawn from ``random_state``, 10 replacement passes) or ``'random'`` (distinct
-    random samples).  With ``n_init > 1`` the run with the lowest inertia is kept.
+    ``init`` is an explicit (n_clusters, n_features) array, ``'k-means++'`` or ``'random'``
+    (both with scikit-learn's RNG call sequence, so a seeded fit picks the same seeds), or
+    ``'furthest_sum'`` (start index drawn from ``random_state``, 10 replacement passes).
+    With ``n_init > 1`` the run with the lowest inertia is kept (sklearn's selection rule).
     """
 
     def __init__(self, n_clusters=8, init='furthest_sum', n_init=1, max_iter=300, tol=1e-4,
@@ -156,17 +232,22 @@ class KMeans():
         self.random_state = random_state
         self.extra_steps = extra_steps
 
-    def _initial_centres(self, X, rng):
+    def _initial_centres(self, X, rng, Xc=None):
         if isinstance(self.init, str):
             if self.init == 'furthest_sum':
                 start = rng.randint(X.shape[0])
                 picks = furthest_sum_centres(X, self.n_clusters, start, self.extra_steps)
                 return X[picks].copy()
-            if self.init == 'random':
-                picks = rng.permutation(X.shape[0])[:self.n_clusters]
+            if self.init == 'k-means++':
+                # sklearn seeds on the mean-centred data (_kmeans.py:1486-1512)
+                _, picks = kmeans_plusplus(Xc, self.n_clusters, random_state=rng)
                 return X[picks].copy()
-            raise ValueError("init must be an array, 'furthest_sum' or 'random'; got %r"
-                             % self.init)
+            if self.init == 'random':
+                n = X.shape[0]
+                picks = rng.choice(n, size=self.n_clusters, replace=False, p=np.ones(n) / n)
+                return X[picks].copy()
+            raise ValueError("init must be an array, 'k-means++', 'furthest_sum' or 'random'; "
+                             "got %r" % self.init)
         init = np.asarray(self.init, dtype=np.float64)
         if init.shape != (self.n_clusters, X.shape[1]):
             raise ValueError('The shape of the initial centers %s does not match the number '
@@ -179,12 +260,17 @@ class KMeans():
         rng = check_random_state(self.random_state)
         n_init = 1 if not isinstance(self.init, str) else max(1, int(self.n_init))
         best = None
-        for _ in range(n_init):
-            centres0 = self._initial_centres(X, rng)
-            result = kmeans_lloyd(X, centres0, tol=self.tol, max_iter=self.max_iter,
-                                  verbose=bool(self.verbose))
-            if best is None or result[2] < best[2]:
-                best = result
+        use_pp = isinstance(self.init, str) and self.init == 'k-means++'
+        Xc = X - X.mean(axis=0) if use_pp else None
+        with be.DeviceCache([Xc] if Xc is not None else []):
+            for _ in range(n_init):
+                centres0 = self._initial_centres(X, rng, Xc)
+                result = kmeans_lloyd(X, centres0, tol=self.tol, max_iter=self.max_iter,
+                                      verbose=bool(self.verbose))
+                # _kmeans.py:1530-1540: lower inertia and a genuinely different clustering
+                if best is None or (result[2] < best[2] and
+                                    not _is_same_clustering(result[0], best[0], self.n_clusters)):
+                    best = result
         self.labels_, self.cluster_centers_, self.inertia_, self.n_iter_ = best
         return self
 

@@ -397,3 +397,44 @@ def test_aa_gram_formulation_matches_streaming(golden):
     close(m.cost, golden['aa/est_random/stats'][0], rtol=1e-6)
     with pytest.raises(ValueError):
         aa._iterate_aa(X, Z0.copy(), C0.copy(), alpha.copy(), formulation='nope', **kw)
+
+
+# ---------------------------------------------------------------- PCA and k-means++ ("next" rows)
+def test_pca_matches_sklearn_full_svd():
+    from sklearn.decomposition import PCA as SkPCA
+    from convex_dim_red import PCA
+    from convex_dim_red.datasets import synthetic_field
+    X = synthetic_field(90, 700, seed=5) + 3.0          # non-zero column means
+    for n in (5, 70):
+        ours = PCA(n_components=n)
+        scores = ours.fit_transform(X)
+        ref = SkPCA(n_components=n, svd_solver='full')
+        ref_scores = ref.fit_transform(X)
+        close(ours.mean_, ref.mean_, rtol=1e-13)
+        close(ours.singular_values_, ref.singular_values_, rtol=1e-9)
+        close(ours.explained_variance_, ref.explained_variance_, rtol=1e-9)
+        close(ours.explained_variance_ratio_, ref.explained_variance_ratio_, rtol=1e-9)
+        close(ours.components_, ref.components_, rtol=0, atol=1e-8)
+        close(scores, ref_scores, rtol=0, atol=1e-7 * np.abs(ref_scores).max())
+        Xn = synthetic_field(11, 700, seed=6) + 3.0
+        close(ours.transform(Xn), ref.transform(Xn), rtol=0, atol=1e-7 * np.abs(ref_scores).max())
+        close(ours.inverse_transform(scores), ref.inverse_transform(ref_scores), rtol=0, atol=1e-7)
+    with pytest.raises(ValueError):
+        PCA(n_components=500).fit(X)
+
+
+def test_kmeans_plusplus_matches_sklearn(golden):
+    from sklearn.cluster import KMeans as SkKMeans, kmeans_plusplus as sk_kmeans_plusplus
+    from convex_dim_red import kmeans_plusplus
+    X = golden['km/X']
+    for seed in (0, 1, 2):
+        c_ref, i_ref = sk_kmeans_plusplus(X, 5, random_state=np.random.RandomState(seed))
+        c, i = kmeans_plusplus(X, 5, random_state=np.random.RandomState(seed))
+        assert np.array_equal(i, i_ref)
+        assert np.array_equal(c, c_ref)
+    for init in ('k-means++', 'random'):
+        ref = SkKMeans(n_clusters=5, init=init, n_init=3, random_state=3, algorithm='lloyd').fit(X.copy())
+        km = KMeans(n_clusters=5, init=init, n_init=3, random_state=3).fit(X)
+        assert np.array_equal(km.labels_, ref.labels_)
+        close(km.inertia_, ref.inertia_, rtol=1e-10)
+        close(km.cluster_centers_, ref.cluster_centers_, rtol=1e-10, atol=1e-12)

@@ -87,6 +87,40 @@ def fit_kmeans_model(X, n_components=2, init='furthest_sum', n_init=1, tolerance
                   max_iter=max_iterations, verbose=verbose, random_state=rng).fit(X)
 
 
+def pca_reduced_sweep(X, n_eofs, component_counts, method='aa', n_init=1, random_state=None,
+                      **fit_kwargs):
+    """PCA reduction followed by a sweep over the number of components -- the
+    ``bin/run_jra55_pca_{aa,gpnh,kmeans}.py`` workflow (config 4 of BASELINE.json): the field
+    is reduced to ``n_eofs`` principal components once, then one model per k is fitted on
+    the scores (both AA solvers limited to one inner iteration and the ``rel_delta_f``
+    stopping rule, as ``bin/run_jra55_pca_aa.py:119-133`` does).
+    Returns ``(pca, {k: model})``."""
+    from .pca import PCA
+    rng = check_random_state(random_state)
+    pca = PCA(n_components=n_eofs)
+    scores = np.ascontiguousarray(pca.fit_transform(X))
+    models = {}
+    for k in component_counts:
+        if method == 'aa':
+            kw = dict(stopping_criterion='rel_delta_f',
+                      dictionary_solver_kwargs=dict(max_iterations=1),
+                      weights_solver_kwargs=dict(max_iterations=1))
+            kw.update(fit_kwargs)
+            models[k] = fit_aa_model(scores, n_components=k, n_init=n_init, random_state=rng, **kw)
+        elif method == 'gpnh':
+            kw = dict(stopping_criterion='rel_delta_f',
+                      weights_solver_kwargs=dict(max_iterations=1))
+            kw.update(fit_kwargs)
+            models[k] = fit_gpnh_model(scores, n_components=k, n_init=n_init, random_state=rng,
+                                       **kw)
+        elif method == 'kmeans':
+            models[k] = fit_kmeans_model(scores, n_components=k, n_init=n_init,
+                                         random_state=rng, **fit_kwargs)
+        else:
+            raise ValueError("method must be 'aa', 'gpnh' or 'kmeans'")
+    return pca, models
+
+
 def evaluate_model(model, training_data, validation_data=None):
     """Training / validation cost and RMSE of a fitted AA or GPNH model
     (bin/run_hadisst_aa.py:226-244, 356-385)."""

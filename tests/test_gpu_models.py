@@ -438,3 +438,21 @@ def test_kmeans_plusplus_matches_sklearn(golden):
         assert np.array_equal(km.labels_, ref.labels_)
         close(km.inertia_, ref.inertia_, rtol=1e-10)
         close(km.cluster_centers_, ref.cluster_centers_, rtol=1e-10, atol=1e-12)
+
+
+def test_pca_reduced_sweep_runs_config4_workflow():
+    """PCA -> AA / k-means sweep on a small JRA-55-like field (BASELINE.json configs[3])."""
+    from convex_dim_red import model_selection as ms
+    from convex_dim_red.datasets import synthetic_field
+    X = synthetic_field(120, 900, seed=8)
+    pca, models = ms.pca_reduced_sweep(X, n_eofs=20, component_counts=(3, 5), method='aa',
+                                       n_init=2, tolerance=1e-6, max_iterations=300, random_state=0)
+    assert pca.components_.shape == (20, 900) and sorted(models) == [3, 5]
+    assert models[5].cost <= models[3].cost + 1e-9         # more archetypes never fit worse here
+    for k, m in models.items():
+        assert m.weights.shape == (120, k) and np.allclose(m.weights.sum(axis=1), 1, 1e-12)
+        assert m.archetypes.shape == (k, 20)
+        # archetypes map back to the grid through the EOFs
+        assert pca.inverse_transform(m.archetypes).shape == (k, 900)
+    _, km = ms.pca_reduced_sweep(X, n_eofs=10, component_counts=(4,), method='kmeans', random_state=1)
+    assert km[4].labels_.shape == (120,)

@@ -180,3 +180,30 @@ def test_model_selection_host_helpers():
     # per-column RMSE, uniformly averaged: sqrt((0 + 4) / 2), sqrt((4 + 16) / 2)
     np.testing.assert_allclose(ms.root_mean_squared_error(a, b),
                                0.5 * (np.sqrt(2.0) + np.sqrt(10.0)))
+
+
+def test_preprocessing_host_helpers():
+    from convex_dim_red import preprocessing as pp
+    lat = np.array([-60.0, 0.0, 60.0, 90.0])
+    np.testing.assert_allclose(pp.latitude_weights(lat, 'cos'), [0.5, 1.0, 0.5, 0.0], atol=1e-15)
+    np.testing.assert_allclose(pp.latitude_weights(lat, 'scos') ** 2, [0.5, 1.0, 0.5, 0.0], atol=1e-15)
+    np.testing.assert_array_equal(pp.latitude_weights(lat, 'none'), np.ones(4))
+    with pytest.raises(ValueError):
+        pp.latitude_weights(lat, 'bogus')
+    rs = np.random.RandomState(0)
+    field = rs.standard_normal((10, 4, 3))
+    field[:, 1, 2] = np.nan                      # a land cell
+    field[3, 0, 0] = np.nan                      # a single missing value also drops the column
+    w = pp.latitude_weights(lat, 'scos')
+    flat = pp.weight_and_flatten(field, w)
+    assert flat.shape == (10, 12) and flat.flags.c_contiguous
+    np.testing.assert_allclose(flat[:, 0 * 3 + 1], field[:, 0, 1] * w[0])
+    valid, missing = pp.drop_missing_features(flat)
+    assert valid.shape == (10, 10) and missing.sum() == 2 and not np.isnan(valid).any()
+    back = pp.restore_features(valid[:2], missing, grid_shape=(4, 3))
+    assert back.shape == (2, 4, 3) and np.isnan(back[:, 1, 2]).all() and np.isnan(back[:, 0, 0]).all()
+    np.testing.assert_allclose(back[:, 2, 1], valid[:2, list(np.where(~missing)[0]).index(2 * 3 + 1)])
+    train, val, missing2, w2 = pp.prepare_field(field, lat, 'scos', validation_frac=0.1)
+    assert train.shape == (9, 10) and val.shape == (1, 10) and np.array_equal(missing, missing2)
+    with pytest.raises(ValueError):
+        pp.weight_and_flatten(field[0], w)

@@ -211,28 +211,48 @@ qp_batched_kernel(const double* __restrict__ A, const double* __restrict__ alpha
         }
         int fe = 1;
         bool searching = active && (f_new > f_max + p.gamma * lam * delta);
+        // Backtracking.  Once sigma_two * lam < sigma_one the safeguarded interpolation of
+        // spg.py:19-33 can only return lam / 2 (its acceptance interval is empty), so the next
+        // four trial steps are known in advance: they are evaluated together (four independent
+        // 8-lane reductions in flight instead of one) and then examined in order, exactly as
+        // the reference would.  This is where the samples with rounding-level Armijo failures
+        // spend their time (~33 halvings per iteration down to lambda_min).
         while (__any_sync(CDR_FULL_MASK, searching)) {
-            double lam_t = lam;
-            if (searching)
-                lam_t = spg_step_length(lam, delta, f_old, f_new, p.sigma_one, p.sigma_two);
-            double xt[KPL];
-            double s = 0.0;
+            const bool halving = p.sigma_two * lam < p.sigma_one;
+            double lt[4];
+            lt[0] = searching ? spg_step_length(lam, delta, f_old, f_new, p.sigma_one, p.sigma_two)
+                              : lam;
+            lt[1] = 0.5 * lt[0];
+            lt[2] = 0.5 * lt[1];
+            lt[3] = 0.5 * lt[2];
+            double st[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
             for (int r = 0; r < KPL; ++r) {
-                xt[r] = xo[r] + lam_t * dk[r];
-                s += xt[r] * (0.5 * (Ax[r] + lam_t * Ad[r]) + b[r]);
-            }
-            const double f_t = group8_sum(s);
-            if (searching) {
-                lam = lam_t;
-                f_new = f_t;
-                fe += 1;
 #pragma unroll
-                for (int r = 0; r < KPL; ++r) xn[r] = xt[r];
-                if (fabs(lam) < p.lambda_min) searching = false;
-                else searching = f_new > f_max + p.gamma * lam * delta;
+                for (int j = 0; j < 4; ++j) {
+                    const double xt = xo[r] + lt[j] * dk[r];
+                    st[j] += xt * (0.5 * (Ax[r] + lt[j] * Ad[r]) + b[r]);
+                }
+            }
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) st[j] += __shfl_xor_sync(CDR_FULL_MASK, st[j], o, 8);
+            }
+            const int nvalid = halving ? 4 : 1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < nvalid && searching) {
+                    lam = lt[j];
+                    f_new = st[j];
+                    fe += 1;
+                    if (fabs(lam) < p.lambda_min) searching = false;
+                    else searching = f_new > f_max + p.gamma * lam * delta;
+                }
             }
         }
+#pragma unroll
+        for (int r = 0; r < KPL; ++r) xn[r] = xo[r] + lam * dk[r];
         // exact A x at the accepted point (gradient and f_old as in spg.py:374-386)
         double Axn[KPL];
         QpMatVec<KPL>::apply(As, arow, xn, Axn, g);

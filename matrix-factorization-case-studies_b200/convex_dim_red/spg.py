@@ -34,6 +34,48 @@ def spg_line_search_cauchy_step_size(beta, sksk, alpha_min=1e-3, alpha_max=1e3):
     return min(alpha_max, max(alpha_min, sksk / beta))
 
 
+class _SpgTrace:
+    """Iteration log in the reference's verbose format (spg.py:159-164, 256-259)."""
+
+    HEADER = '{:<12s} | {:<12s} | {:<13s} | {:<13s} | {:<12s}'
+    ROW = '{:12d} | {:12d} | {: 12.6e} | {: 12.6e} | {: 12.6e}'
+
+    def __init__(self, enabled):
+        self.enabled = bool(enabled)
+
+    def start(self, n_feval, value):
+        if self.enabled:
+            print(self.HEADER.format('n_iter', 'n_feval', 'f', 'conv_crit', 'time'))
+            print('-' * 79)
+            print(self.ROW.format(0, n_feval, value, -1, 0))
+
+    def row(self, *fields):
+        if self.enabled:
+            print(self.ROW.format(*fields))
+
+    def converged(self, iteration):
+        if self.enabled:
+            print('-' * 79)
+            print('*** Converged at iteration {:d} ***'.format(iteration))
+
+
+def _first_step_length(x, grad, project):
+    """Inverse infinity norm of the first (projected) increment (spg.py:178-189)."""
+    if project is None:
+        return 1.0 / np.max(np.abs(grad))
+    reach = np.max(np.abs(project(x - grad) - x))
+    return 1.0 / reach if abs(reach) > 1e-12 else 1.0
+
+
+def _reference_value(history):
+    """Largest stored objective value, scanning with ``>=`` like spg.py:199-203."""
+    best = None
+    for value in history:
+        if best is None or value >= best:
+            best = value
+    return best
+
+
 def spg(f, df, x0, project=None, gamma=1e-4, memory=1,
         sigma_one=0.1, sigma_two=0.9, lambda_min=1e-10,
         alpha0=None, alpha_min=1e-5, alpha_max=1e3,
@@ -42,107 +84,84 @@ def spg(f, df, x0, project=None, gamma=1e-4, memory=1,
         max_iterations=10000, max_feval=1000000):
     """Perform gradient descent steps with non-monotone line-search.
 
-    Same parameters, defaults, warnings and return value
-    ``(sol, fmin, n_iter, n_feval)`` as the reference (spg.py:46-283).
+    Same parameters, defaults, warnings and return value ``(sol, fmin, n_iter, n_feval)``
+    as the reference's ``spg`` (spg.py:46-283): ``f`` / ``df`` are callables returning the
+    objective and its gradient, ``project`` an optional projection onto the feasible set.
+    Works on scalars and on arrays of any type the callables accept.
     """
-    is_multivariate = not np.isscalar(x0)
-    x = x0.copy() if is_multivariate else x0
+    copy = (lambda v: v.copy()) if not np.isscalar(x0) else (lambda v: v)
+    point = copy(x0)
     if project is not None:
-        x = project(x)
+        point = project(point)
 
-    alpha = alpha0
-    f_mem = np.zeros(memory)
-    f_old = f(x)
-    n_feval = 1
+    step = alpha0                      # None -> initialised from the first gradient
+    history = np.zeros(memory)         # zeros, not NaN (spg.py:153)
+    value = f(point)
+    evaluations = 1
+    log = _SpgTrace(verbose)
+    log.start(evaluations, value)
 
-    if verbose:
-        print('{:<12s} | {:<12s} | {:<13s} | {:<13s} | {:<12s}'.format(
-            'n_iter', 'n_feval', 'f', 'conv_crit', 'time'))
-        print('-' * 79)
-        print('{:12d} | {:12d} | {: 12.6e} | {: 12.6e} | {: 12.6e}'.format(
-            0, n_feval, f_old, -1, 0))
+    done = False
+    iteration = -1
+    for iteration in range(max_iterations):
+        tic = time.perf_counter()
+        origin = copy(point)
+        grad = df(point)
+        if step is None:
+            step = _first_step_length(point, grad, project)
 
-    has_converged = False
-    n_iter = -1
-    for n_iter in range(max_iterations):
-        start_time = time.perf_counter()
-        x_old = x.copy() if is_multivariate else x
-        gk = df(x)
-
-        if alpha is None:
-            if project is None:
-                alpha = 1.0 / np.max(np.abs(gk))
-            else:
-                alpha_inv = np.max(np.abs(project(x - gk) - x))
-                alpha = 1.0 / alpha_inv if abs(alpha_inv) > 1e-12 else 1.0
-
-        dk = -alpha * gk
+        direction = -step * grad
         if project is not None:
-            dk = project(x + dk)
-            dk -= x
+            direction = project(point + direction)
+            direction -= point
 
-        f_mem = np.roll(f_mem, 1)
-        f_mem[0] = f_old
-        f_max = None
-        for previous_value in f_mem:
-            if f_max is None or previous_value >= f_max:
-                f_max = previous_value
+        history = np.roll(history, 1)
+        history[0] = value
+        ceiling = _reference_value(history)
 
-        delta = np.sum(dk * gk)
+        slope = np.sum(direction * grad)
         lam = 1
-        x = x_old + dk
-        f_new = f(x)
-        n_feval += 1
-
-        while f_new > f_max + gamma * lam * delta:
-            lam = spg_line_search_step_length(
-                lam, delta, f_old, f_new, sigma_one=sigma_one, sigma_two=sigma_two)
-            x = x_old + lam * dk
-            f_new = f(x)
-            n_feval += 1
+        point = origin + direction
+        trial = f(point)
+        evaluations += 1
+        while trial > ceiling + gamma * lam * slope:
+            lam = spg_line_search_step_length(lam, slope, value, trial,
+                                              sigma_one=sigma_one, sigma_two=sigma_two)
+            point = origin + lam * direction
+            trial = f(point)
+            evaluations += 1
             if abs(lam) < lambda_min:
                 warnings.warn('step size below tolerance in SPG line search', UserWarning)
                 break
 
-        yk = gk.copy() if is_multivariate else gk
-        gk = df(x)
-        yk = gk - yk
+        previous_grad = copy(grad)
+        grad = df(point)
+        change = grad - previous_grad
+        step = spg_line_search_cauchy_step_size(
+            lam * np.sum(direction * change), lam ** 2 * np.sum(direction * direction),
+            alpha_min=alpha_min, alpha_max=alpha_max)
 
-        sksk = lam ** 2 * np.sum(dk * dk)
-        betak = lam * np.sum(dk * yk)
-        alpha = spg_line_search_cauchy_step_size(
-            betak, sksk, alpha_min=alpha_min, alpha_max=alpha_max)
+        value = f(point)
+        evaluations += 1
 
-        f_old = f(x)
-        n_feval += 1
+        residual = -grad if project is None else project(point - grad) - point
+        residual_norm = np.sum(residual ** 2) ** 0.5
+        log.row(iteration + 1, evaluations, value, residual_norm, time.perf_counter() - tic)
 
-        res = -gk if project is None else project(x - gk) - x
-        res_norm = np.sum(res ** 2) ** 0.5
-        end_time = time.perf_counter()
-
-        if verbose:
-            print('{:12d} | {:12d} | {: 12.6e} | {: 12.6e} | {: 12.6e}'.format(
-                n_iter + 1, n_feval, f_old, res_norm, end_time - start_time))
-
-        has_converged = res_norm < epsilon_two
+        done = residual_norm < epsilon_two
         if use_infinity_norm:
-            has_converged = has_converged or np.max(np.abs(res)) < epsilon_one
-
-        if has_converged:
-            if verbose:
-                print('-' * 79)
-                print('*** Converged at iteration {:d} ***'.format(n_iter + 1))
+            done = done or np.max(np.abs(residual)) < epsilon_one
+        if done:
+            log.converged(iteration + 1)
+            break
+        if evaluations > max_feval:
+            warnings.warn('maximum number of function evaluations exceeded in SPG', UserWarning)
             break
 
-        if n_feval > max_feval:
-            warnings.warn('maximum number of function evaluations exceeded in SPG',
-                          UserWarning)
-            break
-
-    if n_iter == max_iterations - 1 and not has_converged:
+    if iteration == max_iterations - 1 and not done:
         warnings.warn('maximum number of iterations exceeded in SPG', UserWarning)
 
-    return x, f_old, n_iter, n_feval
+    return point, value, iteration, evaluations
 
 
 def quad_simplex_spg(A, b, x0, gamma=1e-4, memory=1,

@@ -66,31 +66,78 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    """SM clock / throttle-reason samples while the GPU is under load.
+
+    NVML (a few hundred samples per second) when `pynvml` works, otherwise one
+    `nvidia-smi` query every 0.2 s (the recipe's clocks line)."""
 
     QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
              'clocks_event_reasons.sw_power_cap')
+    REASON_BITS = {'sw_power_cap': 0x4, 'hw_slowdown': 0x8, 'sw_thermal_slowdown': 0x20,
+                   'hw_thermal_slowdown': 0x40}
 
     def __init__(self, index=0):
         self.index = index
-        self.samples = []
+        self.sm, self.sm_max, self.reasons = [], [], set()
+        self.source = None
         self._stop = threading.Event()
         self._thread = None
+        self._nvml = None
 
-    def _loop(self):
+    def _open_nvml(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            index = self.index
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+            if visible:
+                index = int(visible.split(',')[self.index])
+            handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            reasons_fn = getattr(pynvml, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+                getattr(pynvml, 'nvmlDeviceGetCurrentClocksThrottleReasons')
+            smax = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+            return pynvml, handle, reasons_fn, smax
+        except Exception:
+            return None
+
+    def _loop_nvml(self):
+        pynvml, handle, reasons_fn, smax = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)))
+                self.sm_max.append(smax)
+                mask = int(reasons_fn(handle))
+                for name, bit in self.REASON_BITS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.005)
+
+    def _loop_smi(self):
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         while not self._stop.is_set():
             try:
                 out = subprocess.check_output(
                     ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
                      '--format=csv,noheader,nounits'], timeout=5).decode().strip()
-                self.samples.append([v.strip() for v in out.split(',')])
+                vals = [v.strip() for v in out.split(',')]
+                self.sm.append(float(vals[0]))
+                self.sm_max.append(float(vals[1]))
+                for name, val in zip(names, vals[2:6]):
+                    if val.lower().startswith('active'):
+                        self.reasons.add(name)
             except Exception:
                 pass
             self._stop.wait(0.2)
 
     def __enter__(self):
-        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._nvml = self._open_nvml()
+        self.source = 'nvml' if self._nvml else 'nvidia-smi'
+        self._thread = threading.Thread(target=self._loop_nvml if self._nvml else self._loop_smi,
+                                        daemon=True)
         self._thread.start()
         return self
 
@@ -99,20 +146,9 @@ class ClockSampler:
         self._thread.join(timeout=6)
 
     def summary(self):
-        sm, smax, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for s in self.samples:
-            try:
-                sm.append(float(s[0]))
-                smax.append(float(s[1]))
-            except (ValueError, IndexError):
-                continue
-            for name, val in zip(names, s[2:6]):
-                if val.lower().startswith('active'):
-                    reasons.add(name)
-        return {'sm_mhz': float(np.median(sm)) if sm else None,
-                'sm_max_mhz': float(np.max(smax)) if smax else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+        return {'sm_mhz': float(np.median(self.sm)) if self.sm else None,
+                'sm_max_mhz': float(np.max(self.sm_max)) if self.sm_max else None,
+                'reasons': sorted(self.reasons), 'samples': len(self.sm), 'source': self.source}
 
 
 def make_problem(args, rank=0, world=1):

@@ -71,6 +71,11 @@ class Comm:
         mine = scratch[self.world]
         mine[:, :sizes[self.rank]].copy_(local[:, :sizes[self.rank]])
         self._dist.all_gather([scratch[r] for r in range(self.world)], mine, group=self.group)
+        if min(sizes) == nmax:
+            # equal shards: one strided copy (world, k, n) -> (k, world * n)
+            out.as_strided((k, self.world, nmax), (out.stride(0), nmax, 1)).copy_(
+                scratch[:self.world].permute(1, 0, 2))
+            return out
         lo = 0
         for r, n in enumerate(sizes):
             out[:, lo:lo + n].copy_(scratch[r, :, :n])

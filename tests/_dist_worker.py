@@ -71,6 +71,14 @@ def run_gloo(out):
     np.testing.assert_allclose(full[:, :T].numpy(), C0.dot(X).dot(X.T), rtol=1e-12, atol=1e-9)
     assert float(full[:, T:].abs().sum()) == 0.0
 
+    # equal shards take the single strided-copy path
+    eq = torch.arange(k * 7, dtype=torch.float64).reshape(k, 7) + 100.0 * rank
+    full_eq = torch.zeros((k, 20), dtype=torch.float64)
+    comm.allgather_columns(eq, full_eq, [7, 7])
+    want = torch.cat([torch.arange(k * 7, dtype=torch.float64).reshape(k, 7) + 100.0 * r
+                      for r in range(world)], dim=1)
+    assert torch.equal(full_eq[:, :14], want) and float(full_eq[:, 14:].abs().sum()) == 0.0
+
     rows = comm.allgather_rows(Zl)
     assert np.array_equal(rows, Z0)
     mx = torch.tensor([float(rank)], dtype=torch.float64)

@@ -155,18 +155,18 @@ def make_problem(args, rank=0, world=1):
     """Host-generated inputs, identical for the CUDA path and the CPU arm
     (BASELINE.md section 3).  Each rank owns a full slab of `rows` samples."""
     from convex_dim_red.datasets import synthetic_field
-    from oracle import convex_oracle as orc
+    from convex_dim_red.stochastic_matrices import right_stochastic_matrix
     T, d, k = args.rows, args.features, args.components
     X = synthetic_field(T, d, seed=rank)
     rs = np.random.RandomState(1000 + rank)
     if args.workload == 'gpnh':
         # the dictionary is replicated: every rank draws the same one
         W0 = np.sqrt(0.4 / k) * np.random.RandomState(0).randn(d, k)
-        Z0 = orc.right_stochastic_matrix((T, k), rs)
+        Z0 = right_stochastic_matrix((T, k), rs)
         return X, Z0, W0
     # the dictionary (k x total samples) is replicated; the weights are this rank's rows
-    C0 = orc.right_stochastic_matrix((k, T * world), np.random.RandomState(7))
-    Z0 = orc.right_stochastic_matrix((T, k), rs)
+    C0 = right_stochastic_matrix((k, T * world), np.random.RandomState(7))
+    Z0 = right_stochastic_matrix((T, k), rs)
     return X, Z0, C0
 
 

@@ -190,6 +190,7 @@ def zeros(*shape, dtype=None):
 
 
 _RESIDENT = {}
+_RESIDENT_DERIVED = {}      # (key of a resident array, name) -> device tensor derived from it
 
 
 def _cache_key(a):
@@ -217,6 +218,21 @@ class DeviceCache:
     def __exit__(self, *exc):
         for key in self.keys:
             _RESIDENT.pop(key, None)
+            for dkey in [k for k in _RESIDENT_DERIVED if k[0] == key]:
+                _RESIDENT_DERIVED.pop(dkey, None)
+
+
+def resident_derived(a, name, builder):
+    """``builder()`` for a host array, memoised while the array is resident (e.g. its Gram
+    matrix, shared by the FurthestSum initialisations of all restarts)."""
+    if isinstance(a, np.ndarray) and _RESIDENT:
+        key = _cache_key(a)
+        if key in _RESIDENT:
+            dkey = (key, name)
+            if dkey not in _RESIDENT_DERIVED:
+                _RESIDENT_DERIVED[dkey] = builder()
+            return _RESIDENT_DERIVED[dkey]
+    return builder()
 
 
 def _upload_padded(a):

@@ -413,9 +413,12 @@ class _LazyKernel:
 
     def device(self):
         if self._K is None:
-            Xd = self._data_device if self._data_device is not None else \
-                be.to_device_padded(self._data)
-            self._K = be.gram(Xd, self._data.shape[0], self._data.shape[1])
+            def build():
+                Xd = self._data_device if self._data_device is not None else \
+                    be.to_device_padded(self._data)
+                return be.gram(Xd, self._data.shape[0], self._data.shape[1])
+            # shared by all restarts of fit_aa_model while the data are resident
+            self._K = be.resident_derived(self._data, 'gram', build)
         return self._K
 
 

@@ -6,7 +6,7 @@ from convex_dim_red import _backend as be
 from convex_dim_red.archetypal_analysis import _AaEngine
 from convex_dim_red.gpnh_convex_coding import _GpnhEngine
 from convex_dim_red.datasets import synthetic_field
-from oracle import convex_oracle as orc
+from convex_dim_red import stochastic_matrices as orc
 T, d, k = 1620, 44000, 8
 X = synthetic_field(T, d, seed=0)
 rs = np.random.RandomState(1000)

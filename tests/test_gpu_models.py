@@ -355,6 +355,18 @@ def test_fit_models_keep_the_best_restart(golden):
     res = ms.evaluate_model(best, train, val)
     assert res['training_cost'] == best.cost
     assert res['validation_cost'] > 0 and res['validation_rmse'] > 0 and res['training_rmse'] > 0
+    # FurthestSum restarts share one device Gram matrix while the data are resident
+    fs = ms.fit_aa_model(train, n_components=3, init='furthest_sum', n_init=3, tolerance=1e-6,
+                         max_iterations=40, random_state=2)
+    rng = np.random.RandomState(2)
+    fs_costs = []
+    for _ in range(3):
+        m = cdr.ArchetypalAnalysis(n_components=3, init='furthest_sum', tolerance=1e-6,
+                                   max_iterations=40, random_state=rng,
+                                   dictionary_solver_kwargs=dict(max_iterations=1))
+        m.fit_transform(train)
+        fs_costs.append(m.cost)
+    assert fs.cost == min(fs_costs)
     g = ms.fit_gpnh_model(train, n_components=3, lambda_W=0.1, n_init=3, max_iterations=40,
                           random_state=1)
     assert g.dictionary.shape == (X.shape[1], 3) and g.cost > 0

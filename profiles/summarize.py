@@ -59,7 +59,8 @@ def kernels(rep, out):
             tot += v * scale
         traffic.setdefault(name, []).append(tot)
     with open('profiles/ncu_traffic.json', 'w') as fh:
-        json.dump({'source': rep + ' (ncu --set full, per launch, read + write)',
+        json.dump({'source': out + ' (ncu --set full --clock-control none, dram__bytes_read.sum + '
+                             'dram__bytes_write.sum per launch)',
                    'dram_bytes_per_launch': {k: sum(v) / len(v) for k, v in traffic.items()}}, fh,
                   indent=1)
     with open(out, 'w') as fh:

@@ -90,7 +90,6 @@ class _GpnhEngine:
         self.comm.allreduce_sum(n_tot)
         self.T_total = int(n_tot.item())
         self.lib = be.library()
-        self._graph = None
 
     # -- small products -----------------------------------------------------
     def _desc_ZtZ(self):

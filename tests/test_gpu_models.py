@@ -468,3 +468,38 @@ def test_pca_reduced_sweep_runs_config4_workflow():
         assert pca.inverse_transform(m.archetypes).shape == (k, 900)
     _, km = ms.pca_reduced_sweep(X, n_eofs=10, component_counts=(4,), method='kmeans', random_state=1)
     assert km[4].labels_.shape == (120,)
+
+
+# ---------------------------------------------------------------- degenerate shapes
+@pytest.mark.parametrize('T,d,k', [(20, 7, 1), (5, 3, 2), (2, 1, 1), (9, 40, 8), (33, 2, 3)])
+def test_tiny_and_degenerate_shapes_match_oracle(T, d, k):
+    """One component, fewer samples than a DMMA tile, a single feature: every kernel must
+    handle ragged / minimal shapes exactly like the reference algorithm."""
+    rs = np.random.RandomState(T * 100 + d * 10 + k)
+    X = rs.standard_normal((T, d))
+    W0 = 0.5 * rs.standard_normal((d, k))
+    Z0 = orc.right_stochastic_matrix((T, k), rs)
+    C0 = orc.right_stochastic_matrix((k, T), rs)
+    ref = orc.iterate_gpnh(X, Z0.copy(), W0.copy(), lambda_W=0.3, tolerance=1e-12, max_iterations=4)
+    got = gp._iterate_gpnh_convex_coding(X, Z0.copy(), W0.copy(), lambda_W=0.3, tolerance=1e-12,
+                                         max_iterations=4)
+    assert got[3] == ref[3]
+    close(got[2], ref[2], rtol=1e-7, atol=1e-12)
+    close(got[0], ref[0], rtol=0, atol=2e-5)
+    close(got[1], ref[1], rtol=0, atol=2e-5)
+    kw = dict(tolerance=1e-12, max_iterations=4, dictionary_solver_kwargs=dict(max_iterations=2))
+    ref = orc.iterate_aa(X, Z0.copy(), C0.copy(), np.ones(k), **kw)
+    got = aa._iterate_aa(X, Z0.copy(), C0.copy(), np.ones(k), **kw)
+    assert got[4] == ref[4]
+    close(got[3], ref[3], rtol=1e-7, atol=1e-12)
+    close(got[0], ref[0], rtol=0, atol=2e-5)
+    close(got[1], ref[1], rtol=0, atol=2e-5)
+    ref = orc.iterate_kernel_aa(X.dot(X.T), Z0.copy(), C0.copy(), np.ones(k), **kw)
+    got = aa._iterate_kernel_aa(X.dot(X.T), Z0.copy(), C0.copy(), np.ones(k), **kw)
+    close(got[3], ref[3], rtol=1e-7, atol=1e-12)
+    close(got[1], ref[1], rtol=0, atol=2e-5)
+    if T > k:
+        labels, centres, inertia, n_iter = kmeans_lloyd(X, X[:k].copy())
+        rl, rc, ri, rn = orc.kmeans_lloyd(X, X[:k].copy())
+        assert np.array_equal(labels, rl) and n_iter == rn
+        close(centres, rc, rtol=1e-10, atol=1e-12)

@@ -98,6 +98,9 @@ typedef cdr_loop_state cdr_flags;
 const char* cdr_version(void);
 int cdr_device_check(void); /* 0 if the current device is sm_100 */
 unsigned long long cdr_launch_count(void); /* kernels launched by this library so far */
+/* host-only: kernel choice and tile geometry of the two streaming passes for a shape
+ * (12 ints, see stream_gemm.cu); lets the dispatch logic be tested without a GPU */
+int cdr_debug_stream_plan(int T, int d, int k, int with_epilogue, int* out);
 
 /* ------------------------------------------------------------------ simplex
  * Euclidean projection of each row / column of A onto the probability simplex.

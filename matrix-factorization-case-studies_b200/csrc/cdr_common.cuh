@@ -153,5 +153,6 @@ int run_reduce_features_tma(const double* M, long ldm, const double* X, long ldx
                             int k, double* out, long ldo, void* workspace, size_t workspace_bytes,
                             const cdr_flags* flags, cudaStream_t stream);
 size_t reduce_features_tma_workspace_bytes(int T, int d, int k);
+void tma_stream_plan(int T, int d, int k, int with_epilogue, int* out);
 
 }  // namespace cdr

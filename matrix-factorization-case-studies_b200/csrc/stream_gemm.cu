@@ -500,6 +500,23 @@ extern "C" int cdr_reduce_features(const double* M, long ldm, const double* X, l
     return 0;
 }
 
+// Host-only: which kernels and tile geometry the two passes would use for a shape (no GPU
+// needed; used by the CPU-side tests).  out: 12 ints = {samples: strips?, TC, nstrips, stages,
+// smem bytes; features: strips?, TC, nstrips, stages, smem bytes; direct-kernel sample splits;
+// direct-kernel feature chunks}.
+extern "C" int cdr_debug_stream_plan(int T, int d, int k, int with_epilogue, int* out)
+{
+    CDR_CHECK_ARG(T >= 1 && d >= 1 && k >= 1 && out != nullptr);
+    if (k > CDR_MAX_COMPONENTS) return CDR_ERR_UNSUPPORTED;
+    const int dpad = (d + 31) / 32 * 32;
+    tma_stream_plan(T, d, k, with_epilogue, out);
+    out[10] = samples_nsplit(T, dpad);
+    int nchunk, chunk;
+    features_split(T, dpad, &nchunk, &chunk);
+    out[11] = nchunk;
+    return 0;
+}
+
 extern "C" size_t cdr_gram_workspace_bytes(int T, int d)
 {
     // 64-row slabs use the direct-load kernel; a short last slab (<= 16 rows) may take the

@@ -428,6 +428,41 @@ static int ensure_smem(size_t smem)
     return 0;
 }
 
+// strip width shared by the two strip-owned kernels: a multiple of 16 features, as close to
+// dpad / (waves * #SM) as the unit allows
+static void strip_geometry(int dpad, int tc_max, int* TC, int* nstrips)
+{
+    const int nsm = sm_count();
+    int waves = (dpad + nsm * tc_max - 1) / (nsm * tc_max);
+    if (waves < 1) waves = 1;
+    int tc = (dpad + nsm * waves - 1) / (nsm * waves);
+    tc = (tc + 15) / 16 * 16;
+    if (tc > tc_max) tc = tc_max;
+    *TC = tc;
+    *nstrips = (dpad + tc - 1) / tc;
+}
+
+static int ring_stages(size_t fixed_bytes, size_t stage_bytes)
+{
+    int stages = (int)((kSmemBudget - fixed_bytes) / stage_bytes);
+    return stages > kMaxStages ? kMaxStages : stages;
+}
+
+static size_t samples_fixed_smem(int kp, bool fuse_e)
+{
+    return 128 + (fuse_e ? ((size_t)kp * kp + (size_t)kConsumerWarps * kp * 20) * 8 : 0);
+}
+
+// Strip plan of the reduce over samples; false when the direct-load (split-T) kernels should
+// be used: k > 32, few or narrow strips (Gram-space "X" = K, PCA-reduced data), tiny T, or an
+// epilogue matrix with k > 16.
+static bool samples_strip_plan(int T, int dpad, int k, bool with_epilogue, int* TC, int* nstrips)
+{
+    if (k > 32 || (with_epilogue && k > 16)) return false;
+    strip_geometry(dpad, (k <= 16) ? 512 : 256, TC, nstrips);
+    return !(*nstrips < sm_count() / 2 || *TC < 64 || T < 64);
+}
+
 // returns CDR_TMA_NOT_APPLICABLE when the shape should use the direct-load kernels
 template <int KT, int MAXU, bool FUSE_E>
 static int launch_samples_tma(const double* Lp, long sLi, long sLt, const double* X, long ldx, int T,
@@ -435,10 +470,9 @@ static int launch_samples_tma(const double* Lp, long sLi, long sLt, const double
                               long ldo, const cdr_flags* flags, cudaStream_t stream)
 {
     constexpr int KP = 8 * KT;
-    const size_t fixed = 128 + (FUSE_E ? ((size_t)KP * KP + (size_t)kConsumerWarps * KP * 20) * 8 : 0);
+    const size_t fixed = samples_fixed_smem(KP, FUSE_E);
     const size_t stage = (size_t)kSampTR * (TC + 4) * 8;
-    int stages = (int)((kSmemBudget - fixed) / stage);
-    if (stages > kMaxStages) stages = kMaxStages;
+    const int stages = ring_stages(fixed, stage);
     if (stages < 2) return CDR_TMA_NOT_APPLICABLE;
     const size_t smem = fixed + stages * stage;
     int rc = ensure_smem<reduce_samples_tma_kernel<KT, MAXU, FUSE_E>>(smem);
@@ -455,27 +489,17 @@ int run_reduce_samples_tma(const double* Lp, long sLi, long sLt, const double* X
                            const cdr_flags* flags, cudaStream_t stream)
 {
     if (tma_disabled()) return CDR_TMA_NOT_APPLICABLE;
-    if (k > 32) return CDR_TMA_NOT_APPLICABLE;
     if ((ldx % 2) != 0 || (((uintptr_t)X) & 15) != 0) return CDR_TMA_NOT_APPLICABLE;
     const int dpad = (d + 31) / 32 * 32;
-    const int nsm = sm_count();
-    // strip width: a multiple of 16 features, as close to dpad / (m * #SM) as the unit allows
-    const int tc_max = (k <= 16) ? 512 : 256;
-    int waves = (dpad + nsm * tc_max - 1) / (nsm * tc_max);
-    if (waves < 1) waves = 1;
-    int TC = (dpad + nsm * waves - 1) / (nsm * waves);
-    TC = (TC + 15) / 16 * 16;
-    if (TC > tc_max) TC = tc_max;
-    const int nstrips = (dpad + TC - 1) / TC;
-    // few or narrow strips (Gram-space "X" = K, PCA-reduced data): split-T direct kernel
-    if (nstrips < nsm / 2 || TC < 64 || T < 64) return CDR_TMA_NOT_APPLICABLE;
+    int TC, nstrips;
+    if (!samples_strip_plan(T, dpad, k, E != nullptr, &TC, &nstrips)) return CDR_TMA_NOT_APPLICABLE;
     const int kt = (k + 7) / 8;
 #define CDR_S(KT, MAXU)                                                                          \
     do {                                                                                         \
         if (E != nullptr && KT <= 2)                                                             \
             return launch_samples_tma<KT, MAXU, true>(Lp, sLi, sLt, X, ldx, T, dpad, k, TC,      \
                                                       nstrips, E, out, ldo, flags, stream);      \
-        if (E != nullptr) return CDR_TMA_NOT_APPLICABLE;                                         \
+        if (E != nullptr) return CDR_TMA_NOT_APPLICABLE; /* excluded by the plan */              \
         return launch_samples_tma<KT, MAXU, false>(Lp, sLi, sLt, X, ldx, T, dpad, k, TC, nstrips, \
                                                    nullptr, out, ldo, flags, stream);            \
     } while (0)
@@ -486,34 +510,26 @@ int run_reduce_samples_tma(const double* Lp, long sLi, long sLt, const double* X
 #undef CDR_S
 }
 
-// strip width shared by the two strip-owned kernels: a multiple of 16 features, as close to
-// dpad / (waves * #SM) as the unit allows
-static void strip_geometry(int dpad, int tc_max, int* TC, int* nstrips)
-{
-    const int nsm = sm_count();
-    int waves = (dpad + nsm * tc_max - 1) / (nsm * tc_max);
-    if (waves < 1) waves = 1;
-    int tc = (dpad + nsm * waves - 1) / (nsm * waves);
-    tc = (tc + 15) / 16 * 16;
-    if (tc > tc_max) tc = tc_max;
-    *TC = tc;
-    *nstrips = (dpad + tc - 1) / tc;
-}
-
 constexpr int kFsTcMax = 384;
+
+// Strip plan of the reduce over features (shape only): k <= 16, enough wide strips, and the
+// per-strip partials must stay a small fraction of the bytes of X.
+static bool features_strip_plan(int T, int dpad, int k, int* TC, int* nstrips)
+{
+    if (k > 16) return false;
+    strip_geometry(dpad, kFsTcMax, TC, nstrips);
+    if (*nstrips < sm_count() / 2 || *TC < 64 || T < 64) return false;
+    const int kp = (k + 7) / 8 * 8;
+    return (long)(*nstrips) * kp * 10 <= (long)dpad;
+}
 
 static bool features_strip_ok(const double* M, long ldm, const double* X, long ldx, int T, int d,
                               int k, int* TC, int* nstrips)
 {
-    if (tma_disabled() || k > 16) return false;
+    if (tma_disabled()) return false;
     if ((ldx % 2) != 0 || (ldm % 2) != 0) return false;
     if ((((uintptr_t)X) & 15) != 0 || (((uintptr_t)M) & 15) != 0) return false;
-    const int dpad = (d + 31) / 32 * 32;
-    strip_geometry(dpad, kFsTcMax, TC, nstrips);
-    if (*nstrips < sm_count() / 2 || *TC < 64 || T < 64) return false;
-    // the per-strip partials must stay a small fraction of the bytes of X
-    const int kp = (k + 7) / 8 * 8;
-    return (long)(*nstrips) * kp * 10 <= (long)dpad;
+    return features_strip_plan(T, (d + 31) / 32 * 32, k, TC, nstrips);
 }
 
 template <int KT>
@@ -528,8 +544,7 @@ static int launch_features_strip(const double* M, long ldm, const double* X, lon
     if (workspace == nullptr || workspace_bytes < need) return CDR_ERR_WORKSPACE;
     const size_t fixed = 128 + (size_t)2 * 4 * 2 * 8 * KP * 8;
     const size_t stage = (size_t)kFsTR * (TC + 8) * 8;
-    int stages = (int)((kSmemBudget - fixed) / stage);
-    if (stages > kMaxStages) stages = kMaxStages;
+    const int stages = ring_stages(fixed, stage);
     if (stages < 2) return CDR_TMA_NOT_APPLICABLE;
     const size_t smem = fixed + stages * stage;
     int rc = ensure_smem<reduce_features_strip_kernel<KT, MAXUQ>>(smem);
@@ -553,6 +568,34 @@ size_t reduce_features_tma_workspace_bytes(int T, int d, int k)
     const int kp = (k + 7) / 8 * 8;
     if (k > 16 || (long)nstrips * kp * 10 > (long)dpad) return 0;
     return (size_t)nstrips * T * kp * sizeof(double);
+}
+
+// Host-only description of the strip plans (cdr_debug_stream_plan): out[0..4] samples
+// {uses strips, TC, nstrips, stages, smem bytes}, out[5..9] the same for features.
+void tma_stream_plan(int T, int d, int k, int with_epilogue, int* out)
+{
+    const int dpad = (d + 31) / 32 * 32;
+    const int kp = (k + 7) / 8 * 8;
+    for (int i = 0; i < 10; ++i) out[i] = 0;
+    int TC, nstrips;
+    if (samples_strip_plan(T, dpad, k, with_epilogue != 0, &TC, &nstrips)) {
+        const size_t fixed = samples_fixed_smem(kp, with_epilogue != 0);
+        const size_t stage = (size_t)kSampTR * (TC + 4) * 8;
+        const int stages = ring_stages(fixed, stage);
+        if (stages >= 2) {
+            out[0] = 1; out[1] = TC; out[2] = nstrips; out[3] = stages;
+            out[4] = (int)(fixed + stages * stage);
+        }
+    }
+    if (features_strip_plan(T, dpad, k, &TC, &nstrips)) {
+        const size_t fixed = 128 + (size_t)2 * 4 * 2 * 8 * kp * 8;
+        const size_t stage = (size_t)kFsTR * (TC + 8) * 8;
+        const int stages = ring_stages(fixed, stage);
+        if (stages >= 2) {
+            out[5] = 1; out[6] = TC; out[7] = nstrips; out[8] = stages;
+            out[9] = (int)(fixed + stages * stage);
+        }
+    }
 }
 
 int run_reduce_features_tma(const double* M, long ldm, const double* X, long ldx, int T, int d,

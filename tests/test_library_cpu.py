@@ -170,6 +170,53 @@ def test_workspace_size_queries_are_consistent(lib):
     assert lib.cdr_launch_count() == 0 or lib.cdr_launch_count() > 0
 
 
+def test_stream_plan_invariants(lib):
+    """The host-side dispatch of the two streaming passes (which kernel, strip width, ring depth,
+    shared memory) checked over many shapes without a GPU: strips tile the padded feature axis
+    exactly, every strip is non-empty, the ring fits in shared memory, and the workspace the
+    size queries report covers the per-strip partials the strip kernel writes."""
+    rng = np.random.RandomState(11)
+    shapes = [(1620, 44000), (18000, 44000), (700, 41800), (400, 6000), (64, 9472), (63, 9472),
+              (50000, 100000), (1, 1), (7, 33), (1620, 1620)]
+    shapes += [(int(rng.randint(1, 30000)), int(rng.randint(1, 120000))) for _ in range(150)]
+    out = (ctypes.c_int * 12)()
+    used = {'samples': 0, 'features': 0}
+    for T, d in shapes:
+        dpad = (d + 31) // 32 * 32
+        for k in (1, 3, 8, 9, 16, 17, 24, 32, 33, 64):
+            kp = (k + 7) // 8 * 8
+            for epi in (0, 1):
+                assert lib.cdr_debug_stream_plan(T, d, k, epi, out) == 0
+                s_on, s_tc, s_n, s_st, s_smem, f_on, f_tc, f_n, f_st, f_smem, nsplit, nchunk = out
+                assert nsplit >= 1 and nchunk >= 1
+                assert lib.cdr_reduce_samples_workspace_bytes(T, d, k) >= (nsplit > 1) * nsplit * k * dpad * 8
+                assert lib.cdr_reduce_features_workspace_bytes(T, d, k) >= nchunk * T * kp * 8
+                for on, tc, n, st, smem, tcmax, name in (
+                        (s_on, s_tc, s_n, s_st, s_smem, 512 if k <= 16 else 256, 'samples'),
+                        (f_on, f_tc, f_n, f_st, f_smem, 384, 'features')):
+                    if not on:
+                        continue
+                    used[name] += 1
+                    assert T >= 64 and 64 <= tc <= tcmax and tc % 16 == 0
+                    assert n * tc >= dpad > (n - 1) * tc          # exact cover, no empty strip
+                    assert n >= 148 // 2
+                    assert 2 <= st <= 8 and smem <= 227 * 1024
+                    assert st * 16 * tc * 8 >= 32 * 1024           # enough bytes in flight per SM
+                if s_on:
+                    assert k <= 32 and (not epi or k <= 16)
+                if f_on:
+                    assert k <= 16
+                    assert lib.cdr_reduce_features_workspace_bytes(T, d, k) >= f_n * T * kp * 8
+                    assert f_n * kp * 10 <= dpad                   # partials <= 10 % of X
+        if T % 64 or True:
+            for rows in {64, T % 64} - {0}:
+                lib.cdr_debug_stream_plan(T, d, min(rows, 64), 0, out)
+                if out[5]:
+                    assert lib.cdr_gram_workspace_bytes(T, d) >= out[7] * T * ((rows + 7) // 8 * 8) * 8
+    assert used['samples'] > 100 and used['features'] > 100
+    assert lib.cdr_debug_stream_plan(10, 10, 65, 0, out) != 0
+
+
 def test_model_selection_host_helpers():
     from convex_dim_red import model_selection as ms
     X = np.arange(40, dtype=float).reshape(20, 2)

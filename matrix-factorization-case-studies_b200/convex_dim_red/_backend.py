@@ -359,14 +359,36 @@ def frobenius_sq(X, T, d):
     return out
 
 
-def gram(X, T, d):
-    """K = X X' as a padded (T, round_up(T)) device matrix."""
+GRAM_SLAB_ROWS = 64      # cdr_gram forms K in slabs of this many rows (stream_gemm.cu)
+
+
+def gram(X, T, d, comm=None):
+    """K = X X' as a padded (T, round_up(T)) device matrix.
+
+    With a process group every rank holds the same X (all T rows): the 64-row slabs of K are
+    dealt round-robin to the ranks, each slab computed by the very call ``cdr_gram`` makes for
+    it, and summed into place by one all-reduce (zeros elsewhere, so the sum is exact and K
+    is bit-identical to the single-GPU result).
+    """
     torch = require_cuda()
+    lib = library()
     K = torch.zeros((T, round_up(T)), dtype=torch.float64, device='cuda')
-    nbytes = library().cdr_gram_workspace_bytes(T, d)
+    nbytes = lib.cdr_gram_workspace_bytes(T, d)
     ws = torch.zeros(nbytes // 8 + 1, dtype=torch.float64, device='cuda')
-    check(library().cdr_gram(ptr(X), X.stride(0), T, d, ptr(K), K.stride(0), ptr(ws),
-                             ws.numel() * 8, stream_ptr()), 'cdr_gram')
+    if comm is None or not comm.enabled:
+        check(lib.cdr_gram(ptr(X), X.stride(0), T, d, ptr(K), K.stride(0), ptr(ws),
+                           ws.numel() * 8, stream_ptr()), 'cdr_gram')
+        return K
+    ldx, ldk = X.stride(0), K.stride(0)
+    for slab, r0 in enumerate(range(0, T, GRAM_SLAB_ROWS)):
+        if slab % comm.world != comm.rank:
+            continue
+        rows = min(GRAM_SLAB_ROWS, T - r0)
+        check(lib.cdr_reduce_features(
+            X.data_ptr() + 8 * r0 * ldx, ldx, X.data_ptr(), ldx, T, d, rows,
+            K.data_ptr() + 8 * r0 * ldk, ldk, ptr(ws), ws.numel() * 8, None, stream_ptr()),
+            'cdr_reduce_features')
+    comm.allreduce_sum(K)
     return K
 
 

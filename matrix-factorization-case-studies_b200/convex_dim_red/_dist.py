@@ -82,6 +82,99 @@ class Comm:
             lo += n
         return out
 
+    def device(self):
+        """Where tensors handed to the collectives must live ('cuda' under NCCL)."""
+        if self.enabled and self._dist.get_backend(self.group) == 'nccl':
+            return 'cuda'
+        return 'cpu'
+
+    def sum_scalars(self, values):
+        """Element-wise sum over ranks of a short list of Python floats."""
+        import torch
+        if not self.enabled:
+            return [float(v) for v in values]
+        t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=self.device())
+        return [float(v) for v in self.allreduce_sum(t).cpu()]
+
+    def local_rows(self, n_local):
+        """(first global row, total rows) of this rank's block of ``n_local`` rows; the
+        engines use balanced contiguous blocks (``shard_bounds``), which is checked here."""
+        total = int(round(self.sum_scalars([n_local])[0]))
+        lo, hi = shard_bounds(total, self.world, self.rank)
+        if hi - lo != int(n_local):
+            raise ValueError('rank %d holds %d rows; a balanced split of %d rows over %d ranks '
+                             'gives it %d (see convex_dim_red._dist.shard_bounds)'
+                             % (self.rank, n_local, total, self.world, hi - lo))
+        return lo, total
+
+    def broadcast(self, t, src):
+        """In-place broadcast of a tensor from rank ``src``."""
+        if self.enabled:
+            self._dist.broadcast(t, src=src, group=self.group)
+        return t
+
+    def allgather_row_blocks(self, local, sizes):
+        """Stack the (sizes[r], ld) row blocks of every rank into one (sum(sizes), ld) tensor
+        (a device-to-device all-gather of the local rows of X).  Blocks travel as equal
+        (max(sizes), ld) buffers; with equal shards the receive buffer is the result."""
+        import torch
+        if not self.enabled:
+            return local[:sizes[0]]
+        ld = local.shape[1]
+        nmax = max(sizes)
+        scratch = torch.empty((self.world, nmax, ld), dtype=local.dtype, device=local.device)
+        if local.shape[0] == nmax and local.is_contiguous():
+            mine = local
+        else:
+            mine = torch.zeros((nmax, ld), dtype=local.dtype, device=local.device)
+            mine[:sizes[self.rank]].copy_(local[:sizes[self.rank]])
+        self._dist.all_gather([scratch[r] for r in range(self.world)], mine, group=self.group)
+        if min(sizes) == nmax:
+            return scratch.view(self.world * nmax, ld)
+        return torch.cat([scratch[r, :n] for r, n in enumerate(sizes)], dim=0)
+
+    def merge_column_moments(self, mean, var, n_local, n_total):
+        """Column mean and (biased) variance of the stacked rows of all ranks from each
+        rank's own ``mean`` / ``var`` over its ``n_local`` rows:
+        mean = sum_r n_r mean_r / n,  var = sum_r n_r (var_r + (mean_r - mean)^2) / n
+        (two vector all-reduces; no E[x^2] - mean^2 cancellation)."""
+        if not self.enabled:
+            return mean, var
+        total_mean = self.allreduce_sum(mean * float(n_local)) / float(n_total)
+        spread = (var + (mean - total_mean) ** 2) * float(n_local)
+        return total_mean, self.allreduce_sum(spread) / float(n_total)
+
+    def global_top(self, values, offset, n):
+        """The ``n`` largest entries over the concatenated ``values`` (NumPy, one block per
+        rank starting at global index ``offset``): list of ``(value, global_index)``, largest
+        first, lower index first among equals."""
+        values = np.asarray(values)
+        m = min(int(n), values.size)
+        if m > 0:
+            local = np.argsort(-values, kind='stable')[:m]
+            cand = [(float(values[i]), int(offset + i)) for i in local]
+        else:
+            cand = []
+        merged = [c for part in self.allgather_objects(cand) for c in part]
+        merged.sort(key=lambda c: (-c[0], c[1]))
+        return merged[:int(n)]
+
+    def allgather_objects(self, obj):
+        """One picklable object per rank, in rank order."""
+        if not self.enabled:
+            return [obj]
+        parts = [None] * self.world
+        self._dist.all_gather_object(parts, obj, group=self.group)
+        return parts
+
+    def broadcast_object(self, obj, src):
+        """``obj`` of rank ``src`` on every rank."""
+        if not self.enabled:
+            return obj
+        box = [obj if self.rank == src else None]
+        self._dist.broadcast_object_list(box, src=src, group=self.group)
+        return box[0]
+
     def allgather_rows(self, local_np):
         """Gather NumPy row blocks of all ranks (used for the final weights)."""
         if not self.enabled:

@@ -404,10 +404,12 @@ class _LazyKernel:
     an initialisation actually reads it (archetypal_analysis.py:1032 always forms K,
     but init='random' uses nothing but its shape)."""
 
-    def __init__(self, data, data_device=None):
+    def __init__(self, data, data_device=None, comm=None, n_samples=None):
         self._data = data
         self._data_device = data_device
-        self.shape = (data.shape[0], data.shape[0])
+        self._comm = comm if comm is not None and comm.enabled else None
+        n_samples = data.shape[0] if n_samples is None else n_samples
+        self.shape = (n_samples, n_samples)
         self.dtype = np.dtype(np.float64)
         self._K = None
 
@@ -416,6 +418,11 @@ class _LazyKernel:
             def build():
                 Xd = self._data_device if self._data_device is not None else \
                     be.to_device_padded(self._data)
+                if self._comm is not None:
+                    # sample-sharded fit: gather the rows once, deal the slabs of K to the ranks
+                    sizes = shard_sizes(self.shape[0], self._comm.world)
+                    Xd = self._comm.allgather_row_blocks(Xd, sizes)
+                    return be.gram(Xd, self.shape[0], self._data.shape[1], self._comm)
                 return be.gram(Xd, self._data.shape[0], self._data.shape[1])
             # shared by all restarts of fit_aa_model while the data are resident
             self._K = be.resident_derived(self._data, 'gram', build)
@@ -815,20 +822,39 @@ class ArchetypalAnalysis(_AaBase):
     def _aa(self, data, dictionary=None, weights=None, alpha=None,
             update_dictionary=True, update_weights=True,
             update_scale_factors=True, **kwargs):
-        """Perform archetypal analysis (archetypal_analysis.py:1026-1106)."""
+        """Perform archetypal analysis (archetypal_analysis.py:1026-1106).
+
+        ``comm=Comm()`` runs the sample-sharded fit: ``data`` is this rank's balanced row
+        block, initial factors passed in are the full-size ones, the random draws are the
+        single-process ones (same seed on every rank); ``self.weights`` ends up holding the
+        weights of all rows on every rank and the dictionary is replicated."""
+        kwargs = dict(kwargs)
+        comm = kwargs.pop('comm', None)
+        sharded = comm is not None and comm.enabled
         data = np.asarray(data)
         n_samples = data.shape[0]
+        row0 = 0
+        if sharded:
+            row0, n_samples = comm.local_rows(n_samples)
         self._check_params(data.shape[1])
         data64 = np.ascontiguousarray(data, dtype=np.float64)
         Xd = be.to_device_padded(data64)
         # the reference always forms kernel = data.dot(data.T) (:1032); here it is only
         # built (on the device) if the initialisation reads it
-        kernel = _LazyKernel(data64, Xd)
+        kernel = _LazyKernel(data64, Xd, comm, n_samples)
         self._initial_factors(kernel, n_samples, '_aa', dictionary, weights, alpha,
                               update_dictionary, update_weights, kwargs)
         del kernel
-        return self._run(_iterate_aa, data64, update_weights, update_dictionary,
-                         update_scale_factors, data_device=Xd, formulation=self.formulation)
+        if not sharded:
+            return self._run(_iterate_aa, data64, update_weights, update_dictionary,
+                             update_scale_factors, data_device=Xd,
+                             formulation=self.formulation)
+        self.weights = np.ascontiguousarray(self.weights[row0:row0 + data.shape[0]])
+        result = self._run(_iterate_aa, data64, update_weights, update_dictionary,
+                           update_scale_factors, data_device=Xd,
+                           formulation=self.formulation, comm=comm)
+        self.weights = comm.allgather_rows(self.weights)
+        return result
 
     def fit_transform(self, data, dictionary=None, weights=None, alpha=None, **kwargs):
         """Perform archetypal analysis and return transformed data
@@ -838,21 +864,31 @@ class ArchetypalAnalysis(_AaBase):
         self.cost = cost_
         if self.delta != 0:
             self.dictionary = np.dot(np.diag(self.alpha), self.dictionary)
-        self.archetypes = self._archetypes(np.asarray(data, dtype=np.float64))
+        self.archetypes = self._archetypes(np.asarray(data, dtype=np.float64),
+                                           kwargs.get('comm'))
         self.n_iter = n_iter_
         self.avg_time_per_iter = avg_time_per_iter_
         self.cost_deltas = cost_deltas_
         return self.weights
 
-    def _archetypes(self, data):
-        """archetypes = dictionary.dot(data) (archetypal_analysis.py:1144)."""
+    def _archetypes(self, data, comm=None):
+        """archetypes = dictionary.dot(data) (archetypal_analysis.py:1144); with row-sharded
+        data each rank contracts its own columns of the dictionary and the partial k x d
+        products are summed over ranks."""
         T, d = data.shape
         k = self.dictionary.shape[0]
+        sharded = comm is not None and comm.enabled
+        dictionary = self.dictionary
+        if sharded:
+            row0 = comm.local_rows(T)[0]
+            dictionary = np.ascontiguousarray(dictionary[:, row0:row0 + T])
         Xd = be.to_device_padded(data)
-        C = be.to_device_padded(self.dictionary)
+        C = be.to_device_padded(dictionary)
         out = be.zeros(k, Xd.stride(0))
         ws = be.Workspace(T, d, k)
         be.reduce_samples(C, C.stride(0), 1, Xd, T, d, k, out, ws)
+        if sharded:
+            comm.allreduce_sum(out)
         return be.to_host(out, k, d)
 
     def fit(self, data, **kwargs):

@@ -364,8 +364,16 @@ def _initialize_gpnh_convex_coding_dictionary(data, n_components, init='random',
         init = 'random'
     rng = check_random_state(random_state)
     n_samples, n_features = data.shape
+    comm = kwargs.get('comm', None)
+    sharded = comm is not None and comm.enabled     # data = this rank's rows
+    if sharded:
+        n_samples = comm.local_rows(n_samples)[1]
     if init == 'random':
-        avg = np.sqrt(np.abs(data).mean() / n_components)
+        if sharded:
+            mean_abs = comm.sum_scalars([np.abs(data).sum()])[0] / (n_samples * n_features)
+        else:
+            mean_abs = np.abs(data).mean()
+        avg = np.sqrt(mean_abs / n_components)
         return avg * rng.randn(n_features, n_components)
     if init == 'furthest_sum':
         start_index = kwargs.get('start_index', None)
@@ -375,6 +383,11 @@ def _initialize_gpnh_convex_coding_dictionary(data, n_components, init='random',
             start_index = rng.randint(n_samples)
         if exclude is None:
             exclude = np.array([], dtype='i8')
+        if sharded:
+            from .kmeans import furthest_sum_centres, gather_rows
+            selected = furthest_sum_centres(data, n_components, start_index, n_extra_steps,
+                                            exclude, comm=comm)
+            return np.ascontiguousarray(gather_rows(data, selected, comm).T)
         Xd = be.to_device_padded(data)
         K = be.gram(Xd, n_samples, n_features)
         D = dissimilarity_from_gram_device(K, n_samples)
@@ -389,13 +402,15 @@ def _initialize_gpnh_convex_coding_dictionary(data, n_components, init='random',
 
 
 def _initialize_gpnh_convex_coding_weights(data, n_components, init='random',
-                                           random_state=None):
-    """gpnh_convex_coding.py:84-90, 118-129."""
+                                           random_state=None, n_samples=None):
+    """gpnh_convex_coding.py:84-90, 118-129 (``n_samples``: total rows of a sharded fit)."""
     if init is None:
         init = 'random'
     if init in ('furthest_sum', 'random'):
         rng = check_random_state(random_state)
-        return right_stochastic_matrix((data.shape[0], n_components), random_state=rng)
+        if n_samples is None:
+            n_samples = data.shape[0]
+        return right_stochastic_matrix((n_samples, n_components), random_state=rng)
     raise ValueError('Invalid init parameter: got %r instead of one of %r' %
                      (init, INITIALIZATION_METHODS))
 
@@ -407,7 +422,7 @@ def _initialize_gpnh_convex_coding(data, n_components, init='random',
     dictionary = _initialize_gpnh_convex_coding_dictionary(
         data, n_components, init=init, random_state=rng, **kwargs)
     weights = _initialize_gpnh_convex_coding_weights(
-        data, n_components, init=init, random_state=rng)
+        data, n_components, init=init, random_state=rng, n_samples=kwargs.get('n_samples'))
     return dictionary, weights
 
 
@@ -457,8 +472,19 @@ class GPNHConvexCoding():
     def _gpnh_convex_coding(self, data, dictionary=None, weights=None,
                             update_dictionary=True, update_weights=True, **kwargs):
         """Calculate GPNH-regularized convex coding of dataset
-        (gpnh_convex_coding.py:501-572)."""
+        (gpnh_convex_coding.py:501-572).
+
+        ``comm=Comm()`` runs the sample-sharded fit: ``data`` is this rank's balanced row
+        block, initial factors passed in are the full-size ones, the random draws are the
+        single-process ones (same seed on every rank) and ``self.weights`` ends up holding
+        the weights of all rows on every rank."""
         n_samples, n_features = data.shape
+        comm = kwargs.get('comm', None)
+        sharded = comm is not None and comm.enabled
+        row0 = 0
+        if sharded:
+            row0, n_samples = comm.local_rows(n_samples)
+            kwargs = dict(kwargs, n_samples=n_samples)
         self._check_params(n_features)
         k = self.n_components
         if self.init == 'custom':
@@ -469,7 +495,7 @@ class GPNHConvexCoding():
             _check_init_dictionary(dictionary, (n_features, k),
                                    '_gpnh_convex_coding (input dictionary)')
             weights = _initialize_gpnh_convex_coding_weights(
-                data, k, init=self.init, random_state=self.random_state)
+                data, k, init=self.init, random_state=self.random_state, n_samples=n_samples)
         elif update_dictionary and not update_weights:
             _check_init_weights(weights, (n_samples, k), '_gpnh_convex_coding (input weights)')
             dictionary = _initialize_gpnh_convex_coding_dictionary(
@@ -480,6 +506,10 @@ class GPNHConvexCoding():
 
         self.weights = np.array(weights, dtype=np.float64)
         self.dictionary = np.array(dictionary, dtype=np.float64)
+        extra = {}
+        if sharded:
+            self.weights = np.ascontiguousarray(self.weights[row0:row0 + data.shape[0]])
+            extra['comm'] = comm
 
         self.weights, self.dictionary, cost, n_iter, avg_time_per_iter, cost_deltas = \
             _iterate_gpnh_convex_coding(
@@ -490,7 +520,9 @@ class GPNHConvexCoding():
                 require_monotonic_cost_decrease=self.require_monotonic_cost_decrease,
                 stopping_criterion=self.stopping_criterion,
                 weights_solver_kwargs=self.weights_solver_kwargs,
-                dictionary_solver_kwargs=self.dictionary_solver_kwargs)
+                dictionary_solver_kwargs=self.dictionary_solver_kwargs, **extra)
+        if sharded:
+            self.weights = comm.allgather_rows(self.weights)
 
         if n_iter == self.max_iterations and self.tolerance > 0:
             warnings.warn('Maximum number of iterations %d reached.' %

@@ -10,31 +10,75 @@ label-equality / centre-shift stopping rule and the final E-step.  The two
 passes over the data per iteration are the streaming contractions
 ``cdr_reduce_features`` (x.c for all samples and centres) and
 ``cdr_reduce_samples`` (per-cluster sums through a one-hot matrix).
+
+Sample-sharded fits (``comm=Comm()``, one process per GPU, each holding a contiguous block
+of rows): assignment is local; the per-cluster sums (k x d), the counts
+and the changed-label count are summed over ranks; the column mean / variance are merged
+from per-rank moments; empty clusters are moved onto the globally farthest samples; the
+centre update is replicated.  FurthestSum seeding all-gathers the rows once and deals the
+slabs of the Gram matrix to the ranks.
 """
 
 import numpy as np
 from sklearn.utils import check_random_state
 
 from . import _backend as be
+from ._dist import Comm
 from .furthest_sum import dissimilarity_from_gram_device, furthest_sum_device
 
 
-def furthest_sum_centres(X, n_clusters, start_index, extra_steps=10, exclude=None):
+def _group(comm):
+    return comm if comm is not None else Comm(enabled=False)
+
+
+def _row_layout(n_local, comm):
+    """(sizes of all ranks' row blocks, first global row of this rank, total rows)."""
+    sizes = [int(n) for n in comm.allgather_objects(int(n_local))]
+    return sizes, sum(sizes[:comm.rank]), sum(sizes)
+
+
+def furthest_sum_centres(X, n_clusters, start_index, extra_steps=10, exclude=None, comm=None):
     """Indices of the FurthestSum picks on the rows of X (distances from the Gram matrix,
-    as the estimators build them: archetypal_analysis.py:96-100)."""
+    as the estimators build them: archetypal_analysis.py:96-100).  With a process group X
+    is this rank's row block and the indices are global; every rank gets the same picks."""
+    comm = _group(comm)
     X = np.ascontiguousarray(X, dtype=np.float64)
     T, d = X.shape
     Xd = be.to_device_padded(X)
-    K = be.gram(Xd, T, d)
+    if comm.enabled:
+        sizes, _, T = _row_layout(T, comm)
+        Xd = comm.allgather_row_blocks(Xd, sizes)
+    K = be.gram(Xd, T, d, comm)
     D = dissimilarity_from_gram_device(K, T)
     return furthest_sum_device(D, T, n_clusters, start_index, exclude, extra_steps)
 
 
-def kmeans_lloyd(X, init_centres, tol=1e-4, max_iter=300, verbose=False):
+def gather_rows(X, picks, comm=None):
+    """Rows ``picks`` (global indices) of the row-sharded matrix X on every rank: each rank
+    fills in the rows it owns and a sum all-reduce completes the rest."""
+    comm = _group(comm)
+    X = np.asarray(X)
+    if not comm.enabled:
+        return np.array(X[np.asarray(picks)], dtype=np.float64)
+    torch = be.require_cuda()
+    _, lo, _ = _row_layout(X.shape[0], comm)
+    rows = np.zeros((len(picks), X.shape[1]))
+    for i, g in enumerate(picks):
+        if lo <= g < lo + X.shape[0]:
+            rows[i] = X[int(g) - lo]
+    out = torch.from_numpy(rows).cuda()
+    comm.allreduce_sum(out)
+    return out.cpu().numpy()
+
+
+def kmeans_lloyd(X, init_centres, tol=1e-4, max_iter=300, verbose=False, comm=None):
     """``KMeans(init=init_centres, n_init=1, algorithm='lloyd').fit(X)``.
 
-    Returns ``(labels int32[T], centres k x d, inertia, n_iter)``.
+    Returns ``(labels int32[T], centres k x d, inertia, n_iter)``.  With a process group X is
+    this rank's row block and the labels are those of its rows; centres, inertia and n_iter
+    are global and identical on all ranks.
     """
+    comm = _group(comm)
     torch = be.require_cuda()
     lib = be.library()
     X = np.ascontiguousarray(X, dtype=np.float64)
@@ -53,6 +97,9 @@ def kmeans_lloyd(X, init_centres, tol=1e-4, max_iter=300, verbose=False):
     var = be.zeros(ldx)
     be.check(lib.cdr_column_moments(Xd.data_ptr(), ldx, T, d, mean.data_ptr(), var.data_ptr(), s()),
              'cdr_column_moments')
+    if comm.enabled:
+        layout, row0, n_total = _row_layout(T, comm)
+        mean, var = comm.merge_column_moments(mean, var, T, n_total)
     tol_abs = float(np.mean(var[:d].cpu().numpy()) * tol)
     be.check(lib.cdr_center_columns(Xd.data_ptr(), ldx, T, d, mean.data_ptr(), -1.0, s()),
              'cdr_center_columns')
@@ -67,20 +114,41 @@ def kmeans_lloyd(X, init_centres, tol=1e-4, max_iter=300, verbose=False):
     cnorm = be.zeros(k)
     shift = be.zeros(k)
     dist = be.zeros(T)
-    counts = torch.zeros(k, dtype=torch.int32, device='cuda')
-    changed = torch.zeros(1, dtype=torch.int32, device='cuda')
+    tally = torch.zeros(k + 1, dtype=torch.int32, device='cuda')   # counts | changed labels
+    counts, changed = tally[:k], tally[k:]
     ws = be.Workspace(T, d, k)
 
     def e_step():
         be.check(lib.cdr_row_sqnorms(centres.data_ptr(), ldx, k, d, cnorm.data_ptr(), s()),
                  'cdr_row_sqnorms')
         be.reduce_features(centres, Xd, T, d, k, xct, ws)
-        counts.zero_()
-        changed.zero_()
+        tally.zero_()
         be.check(lib.cdr_kmeans_labels(xct.data_ptr(), ldt, cnorm.data_ptr(), T, k,
                                        labels.data_ptr(), onehot.data_ptr(), ldt,
                                        counts.data_ptr(), changed.data_ptr(), s()),
                  'cdr_kmeans_labels')
+        comm.allreduce_sum(tally)
+
+    def relocate_sharded(empty, weights):
+        """Empty clusters -> the globally farthest samples (the owner of each sample
+        broadcasts its row and current label)."""
+        sq_distances()
+        far = comm.global_top(dist.cpu().numpy(), row0, empty.size)
+        if not far or far[0][0] == 0:
+            return
+        row = be.zeros(ldx)
+        for (_, g), cid in zip(far, empty):
+            owner = next(r for r in range(comm.world) if g < sum(layout[:r + 1]))
+            old = None
+            if comm.rank == owner:
+                row.copy_(Xd[g - row0, :])
+                old = int(labels[g - row0].item())
+            comm.broadcast(row, owner)
+            old = comm.broadcast_object(old, owner)
+            sums[old, :] -= row
+            sums[int(cid), :] = row
+            weights[int(cid)] = 1.0
+            weights[old] -= 1.0
 
     def sq_distances():
         be.check(lib.cdr_kmeans_sqdist(Xd.data_ptr(), ldx, T, d, centres.data_ptr(), ldx,
@@ -93,9 +161,13 @@ def kmeans_lloyd(X, init_centres, tol=1e-4, max_iter=300, verbose=False):
         n_iter = it + 1
         e_step()
         be.reduce_samples(onehot, ldt, 1, Xd, T, d, k, sums, ws)
+        comm.allreduce_sum(sums)
         weights = counts.to(torch.float64)
         host_counts = counts.cpu().numpy()
-        if (host_counts == 0).any():
+        if comm.enabled:
+            if (host_counts == 0).any():
+                relocate_sharded(np.where(host_counts == 0)[0], weights)
+        elif (host_counts == 0).any():
             # _k_means_common.pyx:167-212 (rare): move empty clusters onto the samples
             # farthest from their current centres
             empty = np.where(host_counts == 0)[0]
@@ -129,6 +201,7 @@ def kmeans_lloyd(X, init_centres, tol=1e-4, max_iter=300, verbose=False):
     sq_distances()
     total = be.zeros(1)
     be.check(lib.cdr_sum_vector(dist.data_ptr(), T, total.data_ptr(), s()), 'cdr_sum_vector')
+    comm.allreduce_sum(total)
     inertia = float(total.item())
     be.check(lib.cdr_center_columns(centres.data_ptr(), ldx, k, d, mean.data_ptr(), 1.0, s()),
              'cdr_center_columns')
@@ -219,6 +292,10 @@ class KMeans():
     (both with scikit-learn's RNG call sequence, so a seeded fit picks the same seeds), or
     ``'furthest_sum'`` (start index drawn from ``random_state``, 10 replacement passes).
     With ``n_init > 1`` the run with the lowest inertia is kept (sklearn's selection rule).
+
+    ``fit(X_local, comm=Comm())`` is the sample-sharded fit: every rank passes its contiguous
+    block of rows (rank order = row order) and the same ``random_state``; ``labels_`` then
+    holds the labels of all rows on every rank.  ``init='k-means++'`` is single-GPU only.
     """
 
     def __init__(self, n_clusters=8, init='furthest_sum', n_init=1, max_iter=300, tol=1e-4,
@@ -232,7 +309,20 @@ class KMeans():
         self.random_state = random_state
         self.extra_steps = extra_steps
 
-    def _initial_centres(self, X, rng, Xc=None):
+    def _initial_centres(self, X, rng, Xc=None, comm=None):
+        if comm is not None and comm.enabled and isinstance(self.init, str):
+            n_total = _row_layout(X.shape[0], comm)[2]
+            if self.init == 'furthest_sum':
+                start = rng.randint(n_total)
+                picks = furthest_sum_centres(X, self.n_clusters, start, self.extra_steps,
+                                             comm=comm)
+            elif self.init == 'random':
+                picks = rng.choice(n_total, size=self.n_clusters, replace=False,
+                                   p=np.ones(n_total) / n_total)
+            else:
+                raise NotImplementedError("sample-sharded k-means supports init = array, "
+                                          "'furthest_sum' or 'random'; got %r" % self.init)
+            return gather_rows(X, picks, comm)
         if isinstance(self.init, str):
             if self.init == 'furthest_sum':
                 start = rng.randint(X.shape[0])
@@ -255,18 +345,21 @@ class KMeans():
                              (init.shape, self.n_clusters, X.shape[1]))
         return init
 
-    def fit(self, X, y=None):
+    def fit(self, X, y=None, comm=None):
         X = np.ascontiguousarray(X, dtype=np.float64)
         rng = check_random_state(self.random_state)
         n_init = 1 if not isinstance(self.init, str) else max(1, int(self.n_init))
         best = None
-        use_pp = isinstance(self.init, str) and self.init == 'k-means++'
+        sharded = comm is not None and comm.enabled
+        use_pp = isinstance(self.init, str) and self.init == 'k-means++' and not sharded
         Xc = X - X.mean(axis=0) if use_pp else None
         with be.DeviceCache([Xc] if Xc is not None else []):
             for _ in range(n_init):
-                centres0 = self._initial_centres(X, rng, Xc)
+                centres0 = self._initial_centres(X, rng, Xc, comm)
                 result = kmeans_lloyd(X, centres0, tol=self.tol, max_iter=self.max_iter,
-                                      verbose=bool(self.verbose))
+                                      verbose=bool(self.verbose), comm=comm)
+                if sharded:
+                    result = (comm.allgather_rows(result[0]),) + result[1:]
                 # _kmeans.py:1530-1540: lower inertia and a genuinely different clustering
                 if best is None or (result[2] < best[2] and
                                     not _is_same_clustering(result[0], best[0], self.n_clusters)):

@@ -6,6 +6,14 @@ The reference keeps this logic in its ``bin/`` scripts (``fit_aa_model``
 ``bin/run_hadisst_aa.py:204-209`` and the ``TimeSeriesSplit`` cross-validation ``:213-244``)
 wrapped in xarray / netCDF I/O.  Here the same steps work on plain arrays; the data matrix
 is uploaded to the GPU once and shared by all restarts (``resident``).
+
+Restarts are independent, so with a process group (``comm=Comm()``, one process per GPU) they
+run as replicas: restart i is fitted by rank ``i % world`` and the others only advance the
+shared ``RandomState`` by the draws that restart's initialisation makes, which keeps every
+initial matrix identical to the single-process sequence ("draw all
+initial matrices on the host from the single shared RandomState in the reference's order,
+then farm restarts out to GPUs").  The fit with the lowest cost -- the first one in restart
+order on ties, as the serial strict ``<`` comparison keeps it -- is broadcast to all ranks.
 """
 
 from copy import deepcopy
@@ -39,44 +47,122 @@ def root_mean_squared_error(a, b):
     return float(np.mean(np.sqrt(np.mean((np.asarray(a) - np.asarray(b)) ** 2, axis=0))))
 
 
+def _serial_winner(costs):
+    """Index the serial loop ``if best is None or cost < min_cost`` ends up keeping."""
+    winner = None
+    for index, cost in enumerate(costs):
+        if winner is None or cost < costs[winner]:
+            winner = index
+    return winner
+
+
+def best_of_restarts(n_init, fit_one, skip_one=None, comm=None):
+    """Fit ``n_init`` restarts and return the model with the lowest ``cost``.
+
+    ``fit_one()`` fits one restart (consuming the shared RNG); ``skip_one()`` advances the
+    RNG by exactly the draws ``fit_one`` would make without fitting.  Without a process group
+    this is the reference's loop (bin/run_hadisst_aa.py:154-172); with one, restart i runs on
+    rank ``i % world`` and every rank returns the same winning model.
+    """
+    world, rank = (comm.world, comm.rank) if comm is not None and comm.enabled else (1, 0)
+    if world > 1 and skip_one is None:
+        raise ValueError('replicated restarts need skip_one to keep the RNG sequence')
+    mine = {}                 # restart index -> cost, for the restarts fitted here
+    best_index, best_model = None, None
+    for index in range(n_init):
+        if index % world != rank:
+            skip_one()
+            continue
+        model = fit_one()
+        mine[index] = model.cost
+        if best_index is None or model.cost < mine[best_index]:
+            best_model = deepcopy(model)
+            best_index = index
+    if world == 1:
+        return best_model
+    costs = [None] * n_init
+    for part in comm.allgather_objects(mine):
+        for index, cost in part.items():
+            costs[index] = cost
+    winner = _serial_winner(costs)
+    if winner is None:
+        return None
+    owner = winner % world
+    if rank == owner and best_index != winner:
+        raise RuntimeError('restart selection diverged between ranks')
+    return comm.broadcast_object(best_model if rank == owner else None, owner)
+
+
+def _skip_aa_initialisation(rng, init, n_samples, n_components, delta):
+    """The RNG draws of one ``ArchetypalAnalysis`` initialisation, discarded: dictionary
+    (uniform k x T, or one start index for FurthestSum), weights (uniform T x k), scale
+    factors when delta != 0 (archetypal_analysis.py:51-164 of the reference)."""
+    if init == 'random':
+        rng.uniform(size=(n_components, n_samples))
+    elif init in (None, 'furthest_sum'):
+        rng.randint(n_samples)
+    else:
+        raise ValueError('replicated restarts support init = random or furthest_sum')
+    rng.uniform(size=(n_samples, n_components))
+    if delta != 0:
+        rng.uniform(low=(1 - delta), high=(1 + delta), size=(n_components,))
+
+
+def _skip_gpnh_initialisation(rng, init, n_samples, n_features, n_components):
+    """GPNH counterpart: normal d x k dictionary (or a start index), then uniform weights
+    (gpnh_convex_coding.py:41-143 of the reference)."""
+    if init in (None, 'random'):
+        rng.randn(n_features, n_components)
+    elif init == 'furthest_sum':
+        rng.randint(n_samples)
+    else:
+        raise ValueError('replicated restarts support init = random or furthest_sum')
+    rng.uniform(size=(n_samples, n_components))
+
+
 def fit_aa_model(X, n_components=2, delta=0, init='random', n_init=100,
                  tolerance=1e-6, max_iterations=10000, verbose=False,
-                 random_state=None, **kwargs):
+                 random_state=None, comm=None, **kwargs):
     """Run archetypal analysis ``n_init`` times from one shared RNG and keep the fit with
-    the lowest cost (bin/run_hadisst_aa.py:149-174)."""
+    the lowest cost (bin/run_hadisst_aa.py:149-174).  ``comm`` spreads the restarts over
+    the ranks of a process group; every rank passes the same X and seed."""
     rng = check_random_state(random_state)
     kwargs.setdefault('dictionary_solver_kwargs', dict(max_iterations=1))
-    min_cost = None
-    best_model = None
+    n_samples = np.shape(X)[0]
+
+    def fit_one():
+        model = ArchetypalAnalysis(
+            n_components=n_components, delta=delta, init=init, tolerance=tolerance,
+            max_iterations=max_iterations, verbose=verbose, random_state=rng, **kwargs)
+        model.fit_transform(X)
+        return model
+
+    def skip_one():
+        _skip_aa_initialisation(rng, init, n_samples, n_components, delta)
+
     with resident(X):
-        for _ in range(n_init):
-            model = ArchetypalAnalysis(
-                n_components=n_components, delta=delta, init=init, tolerance=tolerance,
-                max_iterations=max_iterations, verbose=verbose, random_state=rng, **kwargs)
-            model.fit_transform(X)
-            if min_cost is None or model.cost < min_cost:
-                best_model = deepcopy(model)
-                min_cost = model.cost
-    return best_model
+        return best_of_restarts(n_init, fit_one, skip_one, comm)
 
 
 def fit_gpnh_model(X, n_components=2, lambda_W=0, init='random', n_init=100,
                    tolerance=1e-6, max_iterations=10000, verbose=False,
-                   random_state=None, **kwargs):
+                   random_state=None, comm=None, **kwargs):
     """GPNH counterpart (bin/run_hadisst_gpnh.py:149-171)."""
     rng = check_random_state(random_state)
-    min_cost = None
-    best_model = None
+    n_samples, n_features = np.shape(X)
+
+    def fit_one():
+        model = GPNHConvexCoding(
+            n_components=n_components, lambda_W=lambda_W, init=init, tolerance=tolerance,
+            max_iterations=max_iterations, verbose=verbose, random_state=rng, **kwargs)
+        model.fit_transform(X)
+        return model
+
+    def skip_one():
+        _skip_gpnh_initialisation(rng, init, n_samples, n_features, n_components)
+
     with resident(X):
-        for _ in range(n_init):
-            model = GPNHConvexCoding(
-                n_components=n_components, lambda_W=lambda_W, init=init, tolerance=tolerance,
-                max_iterations=max_iterations, verbose=verbose, random_state=rng, **kwargs)
-            model.fit_transform(X)
-            if min_cost is None or model.cost < min_cost:
-                best_model = deepcopy(model)
-                min_cost = model.cost
-    return best_model
+        return best_of_restarts(n_init, fit_one, skip_one, comm)
 
 
 def fit_kmeans_model(X, n_components=2, init='furthest_sum', n_init=1, tolerance=1e-4,

@@ -21,7 +21,20 @@ import torch                      # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 
-def problem(T=203, d=300, k=5, seed=11):
+def problem(T=203, d=300, k=5, seed=11, path=None):
+    """Seeded test problem.  ``path``: load it from / save it to an .npz, so that the worker
+    processes and the test process use bit-identical inputs (the BLAS product inside the
+    generator rounds differently under a different thread count)."""
+    if path is not None and os.path.exists(path):
+        f = np.load(path)
+        return f['X'], f['Z0'], f['W0'], f['C0']
+    made = _generate_problem(T, d, k, seed)
+    if path is not None:
+        np.savez(path, X=made[0], Z0=made[1], W0=made[2], C0=made[3])
+    return made
+
+
+def _generate_problem(T, d, k, seed):
     from oracle import convex_oracle as orc
     from convex_dim_red.datasets import synthetic_field
     X = synthetic_field(T, d, seed=seed)
@@ -30,6 +43,86 @@ def problem(T=203, d=300, k=5, seed=11):
     Z0 = orc.right_stochastic_matrix((T, k), rs)
     C0 = orc.right_stochastic_matrix((k, T), rs)
     return X, Z0, W0, C0
+
+
+DATA = [None]      # path of the shared problem file (--data), if any
+
+
+class _FakeModel:
+    """Stands in for an estimator: its cost is a function of the draws its initialisation
+    takes from the shared RNG, so a wrong draw order changes the winner."""
+
+    def __init__(self, rng, shape):
+        C = rng.uniform(size=shape)
+        Z = rng.uniform(size=shape[::-1])
+        self.cost = float(np.round(np.abs(C.sum() - Z.sum()), 1))    # rounded: forces ties
+        self.draws = (C, Z)
+
+
+def replicated_restarts_check(comm):
+    """best_of_restarts over the group returns, on every rank, exactly the model the serial
+    loop keeps (first minimum, shared RNG sequence), for several restart counts."""
+    from convex_dim_red.model_selection import best_of_restarts, _skip_aa_initialisation
+    shape = (3, 17)
+    for n_init in (1, 2, 5, 8):
+        rng = np.random.RandomState(5)
+        serial = best_of_restarts(n_init, lambda: _FakeModel(rng, shape))
+        serial_state = rng.get_state()[1].copy()
+        rng = np.random.RandomState(5)
+        got = best_of_restarts(
+            n_init, lambda: _FakeModel(rng, shape),
+            lambda: _skip_aa_initialisation(rng, 'random', shape[1], shape[0], 0), comm)
+        assert got.cost == serial.cost
+        assert np.array_equal(got.draws[0], serial.draws[0])
+        assert np.array_equal(got.draws[1], serial.draws[1])
+        assert np.array_equal(rng.get_state()[1], serial_state)
+
+
+def row_helpers_check(comm, X):
+    """Helpers of the row-sharded k-means / FurthestSum / estimator paths on CPU tensors."""
+    from convex_dim_red._dist import shard_bounds, shard_sizes
+    T, d = X.shape
+    rank, world = comm.rank, comm.world
+    lo, hi = shard_bounds(T, world, rank)
+    sizes = shard_sizes(T, world)
+    assert comm.device() == 'cpu'
+    assert comm.local_rows(hi - lo) == (lo, T)
+    try:
+        comm.local_rows(hi - lo + (1 if rank == 0 else -1))     # total unchanged, split wrong
+    except ValueError:
+        pass
+    else:
+        raise AssertionError('unbalanced row blocks must be rejected')
+    assert comm.sum_scalars([1.0, float(rank)]) == [float(world), 1.0]
+
+    # device-side all-gather of row blocks (ragged: 203 rows over 2 ranks)
+    Xl = torch.from_numpy(X[lo:hi].copy())
+    full = comm.allgather_row_blocks(Xl, sizes)
+    assert full.shape == (T, d) and np.array_equal(full.numpy(), X)
+    even = comm.allgather_row_blocks(Xl[:100].contiguous(), [100, 100])
+    assert np.array_equal(even.numpy(), np.concatenate([X[:100], X[102:202]]))
+
+    # column moments merged from per-rank moments (k-means centring and tolerance)
+    Y = X + 50.0                                            # large mean: no cancellation allowed
+    Yl = Y[lo:hi]
+    mean, var = comm.merge_column_moments(torch.from_numpy(Yl.mean(axis=0)),
+                                          torch.from_numpy(Yl.var(axis=0)), hi - lo, T)
+    np.testing.assert_allclose(mean.numpy(), Y.mean(axis=0), rtol=1e-14)
+    np.testing.assert_allclose(var.numpy(), Y.var(axis=0), rtol=1e-11)
+
+    # globally farthest samples (empty-cluster relocation): values with ties across ranks
+    vals = np.round(np.abs(X[:, 0]) * 3.0)
+    got = comm.global_top(vals[lo:hi], lo, 6)
+    order = sorted(range(T), key=lambda i: (-vals[i], i))[:6]
+    assert [g for _, g in got] == order and [v for v, _ in got] == [vals[i] for i in order]
+    assert comm.global_top(vals[lo:hi], lo, 0) == []
+    assert len(comm.global_top(vals[lo:lo + 1], lo, 5)) == world      # fewer rows than asked
+
+    t = torch.full((3,), float(rank))
+    comm.broadcast(t, 1)
+    assert t.tolist() == [1.0, 1.0, 1.0]
+    assert comm.broadcast_object({'rank': rank}, 1) == {'rank': 1}
+    assert comm.allgather_objects(rank) == list(range(world))
 
 
 def run_gloo(out):
@@ -81,6 +174,8 @@ def run_gloo(out):
 
     rows = comm.allgather_rows(Zl)
     assert np.array_equal(rows, Z0)
+    replicated_restarts_check(comm)
+    row_helpers_check(comm, X)
     mx = torch.tensor([float(rank)], dtype=torch.float64)
     comm.allreduce_max(mx)
     assert mx.item() == world - 1
@@ -88,6 +183,55 @@ def run_gloo(out):
         np.savez(out, ok=np.array([1]))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def wider_cases(X, lo, hi, comm=None):
+    """Estimator-level fits, replicated restarts and k-means; run row-sharded over the group
+    by the worker and on one GPU by the test (comm=None), which compares the two."""
+    import warnings
+    from convex_dim_red import ArchetypalAnalysis, GPNHConvexCoding
+    from convex_dim_red.kmeans import KMeans
+    from convex_dim_red.model_selection import fit_aa_model, fit_gpnh_model
+    warnings.simplefilter('ignore', UserWarning)
+    kw = dict(comm=comm) if comm is not None else {}
+    Xl = np.ascontiguousarray(X[lo:hi])
+    res = {}
+
+    m = ArchetypalAnalysis(5, init='furthest_sum', random_state=3, max_iterations=5,
+                           tolerance=1e-12, dictionary_solver_kwargs=dict(max_iterations=1))
+    m.fit_transform(Xl, **kw)
+    res.update(e_aa_Z=m.weights, e_aa_C=m.dictionary, e_aa_A=m.archetypes, e_aa_cost=m.cost)
+    m = GPNHConvexCoding(4, lambda_W=0.1, init='random', random_state=4, max_iterations=5,
+                         tolerance=1e-12)
+    m.fit_transform(Xl, **kw)
+    res.update(e_gp_Z=m.weights, e_gp_W=m.dictionary, e_gp_cost=m.cost)
+    m = GPNHConvexCoding(4, init='furthest_sum', random_state=5, max_iterations=3,
+                         tolerance=1e-12)
+    m.fit_transform(Xl, **kw)
+    res.update(e_gf_Z=m.weights, e_gf_W=m.dictionary, e_gf_cost=m.cost)
+
+    # replicated restarts work on the whole matrix on every rank
+    m = fit_gpnh_model(X, n_components=4, lambda_W=0.05, n_init=3, max_iterations=4,
+                       tolerance=1e-12, random_state=7, **kw)
+    res.update(r_gp_Z=m.weights, r_gp_W=m.dictionary, r_gp_cost=m.cost)
+    m = fit_aa_model(X, n_components=4, init='furthest_sum', n_init=3, max_iterations=4,
+                     tolerance=1e-12, random_state=8, **kw)
+    res.update(r_aa_Z=m.weights, r_aa_C=m.dictionary, r_aa_cost=m.cost)
+
+    for name, init in (('fs', 'furthest_sum'), ('rnd', 'random')):
+        km = KMeans(n_clusters=5, init=init, random_state=1, max_iter=50).fit(Xl, **kw)
+        res.update({'k_%s_labels' % name: km.labels_, 'k_%s_centres' % name: km.cluster_centers_,
+                    'k_%s_inertia' % name: km.inertia_, 'k_%s_n' % name: km.n_iter_})
+    # a centre far from every sample starts empty and is moved onto the farthest sample
+    init = np.concatenate([X[[0, 57, 111, 180]], np.full((1, X.shape[1]), 1e3)])
+    km = KMeans(n_clusters=5, init=init, max_iter=50).fit(Xl, **kw)
+    res.update(k_emp_labels=km.labels_, k_emp_centres=km.cluster_centers_,
+               k_emp_inertia=km.inertia_, k_emp_n=km.n_iter_)
+    return res
+
+
+def wider_nccl_cases(comm, X, lo, hi):
+    return wider_cases(X, lo, hi, comm)
 
 
 def run_nccl(out):
@@ -98,7 +242,7 @@ def run_nccl(out):
     from convex_dim_red import archetypal_analysis as aa
     from convex_dim_red import gpnh_convex_coding as gp
     comm = Comm()
-    X, Z0, W0, C0 = problem(T=403, d=2600, k=8)
+    X, Z0, W0, C0 = problem(T=403, d=2600, k=8, path=DATA[0])
     T = X.shape[0]
     lo, hi = shard_bounds(T, comm.world, comm.rank)
     g = gp._iterate_gpnh_convex_coding(X[lo:hi].copy(), Z0[lo:hi].copy(), W0.copy(), lambda_W=0.2,
@@ -108,8 +252,10 @@ def run_nccl(out):
                        dictionary_solver_kwargs=dict(max_iterations=2), comm=comm)
     Zg = comm.allgather_rows(g[0])
     Za = comm.allgather_rows(a[0])
+    extra = wider_nccl_cases(comm, X, lo, hi)
     if comm.rank == 0:
-        np.savez(out, gZ=Zg, gW=g[1], gcost=g[2], gn=g[3], aZ=Za, aC=a[1], acost=a[3], an=a[4])
+        np.savez(out, gZ=Zg, gW=g[1], gcost=g[2], gn=g[3], aZ=Za, aC=a[1], acost=a[3], an=a[4],
+                 **extra)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -118,5 +264,7 @@ if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('--mode', required=True)
     ap.add_argument('--out', required=True)
+    ap.add_argument('--data', default=None)
     args = ap.parse_args()
+    DATA[0] = args.data
     (run_gloo if args.mode == 'gloo' else run_nccl)(args.out)

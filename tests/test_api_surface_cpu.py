@@ -134,3 +134,57 @@ def test_parameter_validation_happens_before_any_device_work():
     with pytest.raises(ValueError, match='Dissimilarity matrix must be square'):
         cdr.furthest_sum(np.zeros((3, 4)), 2, 0)
     assert cdr.furthest_sum(np.zeros((3, 3)), 0, 0) == []
+
+
+def test_skipped_initialisation_takes_the_same_rng_draws(monkeypatch):
+    """Replicated restarts (model_selection.best_of_restarts) skip the fits of other ranks
+    by discarding the RNG draws their initialisation would take.  The skip functions must
+    advance the RandomState exactly like the real initialisers; FurthestSum's device work is
+    stubbed out (it consumes no random numbers)."""
+    from convex_dim_red import model_selection as ms
+    T, d, k = 23, 31, 4
+    X = np.random.RandomState(0).randn(T, d)
+
+    class Shape:
+        shape = (T, T)
+
+    monkeypatch.setattr(aa, '_kernel_device', lambda kernel: None)
+    monkeypatch.setattr(aa, 'dissimilarity_from_gram_device', lambda K, n: None)
+    monkeypatch.setattr(aa, 'furthest_sum_device', lambda *a, **kw: np.arange(k))
+    monkeypatch.setattr(gp, 'dissimilarity_from_gram_device', lambda K, n: None)
+    monkeypatch.setattr(gp, 'furthest_sum_device', lambda *a, **kw: np.arange(k))
+    monkeypatch.setattr(gp.be, 'to_device_padded', lambda a: None)
+    monkeypatch.setattr(gp.be, 'gram', lambda *a: None)
+
+    def state(rng):
+        st = rng.get_state()
+        return st[1].tobytes(), st[2], st[3], st[4]
+
+    for init in ('random', 'furthest_sum', None):
+        for delta in (0, 0.3):
+            real, skip = np.random.RandomState(3), np.random.RandomState(3)
+            aa._initialize_kernel_aa(Shape(), k, init=init, random_state=real)
+            aa._initialize_kernel_aa_scale_factors_random(k, delta=delta, random_state=real)
+            ms._skip_aa_initialisation(skip, init, T, k, delta)
+            assert state(real) == state(skip), ('aa', init, delta)
+        real, skip = np.random.RandomState(3), np.random.RandomState(3)
+        gp._initialize_gpnh_convex_coding(X, k, init=init, random_state=real)
+        ms._skip_gpnh_initialisation(skip, init, T, d, k)
+        assert state(real) == state(skip), ('gpnh', init)
+    with pytest.raises(ValueError):
+        ms._skip_aa_initialisation(np.random.RandomState(0), 'custom', T, k, 0)
+
+
+def test_best_of_restarts_keeps_the_first_minimum():
+    from convex_dim_red.model_selection import best_of_restarts, _serial_winner
+
+    class M:
+        def __init__(self, cost, tag):
+            self.cost, self.tag = cost, tag
+
+    seq = iter([M(3.0, 'a'), M(1.0, 'b'), M(1.0, 'c'), M(2.0, 'd')])
+    assert best_of_restarts(4, lambda: next(seq)).tag == 'b'
+    assert _serial_winner([3.0, 1.0, 1.0, 2.0]) == 1
+    assert _serial_winner([float('nan'), 1.0]) == 0        # the reference loop never replaces NaN
+    assert _serial_winner([2.0, float('nan'), 1.0]) == 2
+    assert best_of_restarts(0, lambda: None) is None

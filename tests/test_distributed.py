@@ -20,10 +20,12 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _launch(mode, out, nproc=2, timeout=600):
+def _launch(mode, out, nproc=2, timeout=600, data=None):
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(nproc),
            '--master-addr', '127.0.0.1', '--master-port', str(_free_port()), WORKER,
            '--mode', mode, '--out', out]
+    if data is not None:
+        cmd += ['--data', data]
     env = dict(os.environ, OMP_NUM_THREADS='2')
     res = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                          timeout=timeout)
@@ -51,13 +53,14 @@ def test_sharded_engines_nccl_world2(tmp_path):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip('needs two GPUs')
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
-    from _dist_worker import problem
+    from _dist_worker import problem, wider_cases
     from convex_dim_red import archetypal_analysis as aa
     from convex_dim_red import gpnh_convex_coding as gp
     out = str(tmp_path / 'nccl.npz')
-    _launch('nccl', out)
+    data = str(tmp_path / 'problem.npz')
+    X, Z0, W0, C0 = problem(T=403, d=2600, k=8, path=data)     # written here, read by the ranks
+    _launch('nccl', out, data=data)
     got = np.load(out)
-    X, Z0, W0, C0 = problem(T=403, d=2600, k=8)
     g = gp._iterate_gpnh_convex_coding(X, Z0.copy(), W0.copy(), lambda_W=0.2, tolerance=1e-12,
                                        max_iterations=6)
     a = aa._iterate_aa(X, Z0.copy(), C0.copy(), np.ones(8), tolerance=1e-12, max_iterations=6,
@@ -69,3 +72,35 @@ def test_sharded_engines_nccl_world2(tmp_path):
     np.testing.assert_allclose(got['acost'], a[3], rtol=1e-9)
     np.testing.assert_allclose(got['aZ'], a[0], rtol=0, atol=2e-5)
     np.testing.assert_allclose(got['aC'], a[1], rtol=0, atol=2e-5)
+
+    # estimator-level sharded fits, replicated restarts and sharded k-means; all checks run
+    # before the verdict so that one multi-GPU run reports every mismatch
+    want = wider_cases(X, 0, X.shape[0])
+    problems = []
+
+    def check(label, fn):
+        try:
+            fn()
+        except AssertionError as exc:
+            problems.append('%s: %s' % (label, ' '.join(str(exc).split())[:400]))
+
+    for key in ('r_gp_Z', 'r_gp_W', 'r_aa_Z', 'r_aa_C', 'r_gp_cost', 'r_aa_cost'):
+        # the winning restart ran on one GPU from the same initial matrices: identical
+        check(key, lambda key=key: np.testing.assert_array_equal(got[key], want[key]))
+    for key in ('e_aa_cost', 'e_gp_cost', 'e_gf_cost'):
+        check(key, lambda key=key: np.testing.assert_allclose(got[key], want[key], rtol=1e-9))
+    for key in ('e_aa_Z', 'e_aa_C', 'e_gp_Z', 'e_gp_W', 'e_gf_Z', 'e_gf_W'):
+        check(key, lambda key=key: np.testing.assert_allclose(got[key], want[key], rtol=0,
+                                                              atol=2e-5))
+    check('e_aa_A', lambda: np.testing.assert_allclose(got['e_aa_A'], want['e_aa_A'], rtol=0,
+                                                       atol=2e-4))
+    for name in ('fs', 'rnd', 'emp'):
+        check('k_%s_labels' % name, lambda name=name: np.testing.assert_array_equal(
+            got['k_%s_labels' % name], want['k_%s_labels' % name]))
+        check('k_%s_n' % name, lambda name=name: np.testing.assert_array_equal(
+            int(got['k_%s_n' % name]), int(want['k_%s_n' % name])))
+        check('k_%s_centres' % name, lambda name=name: np.testing.assert_allclose(
+            got['k_%s_centres' % name], want['k_%s_centres' % name], rtol=1e-10, atol=1e-10))
+        check('k_%s_inertia' % name, lambda name=name: np.testing.assert_allclose(
+            got['k_%s_inertia' % name], want['k_%s_inertia' % name], rtol=1e-10))
+    assert not problems, '\n'.join(problems)

@@ -39,6 +39,7 @@ extern "C" {
 #define CDR_ERR_INVALID_ARGUMENT (-1)
 #define CDR_ERR_UNSUPPORTED (-2)
 #define CDR_ERR_WORKSPACE (-3)
+#define CDR_ERR_NOT_APPLICABLE (-4) /* fused path does not cover this shape: use the unfused calls */
 
 typedef void* cdr_stream_t; /* cudaStream_t */
 
@@ -279,6 +280,68 @@ int cdr_column_moments(const double* X, long ldx, int T, int d, double* mean, do
                        cdr_stream_t stream);
 int cdr_center_columns(double* X, long ldx, int T, int d, const double* mean, double sign,
                        cdr_stream_t stream);
+
+/* ------------------------------------------------------------------ peer-memory collectives
+ * The exchange steps of the sample-sharded fit as kernels of this
+ * library over NVLink / NVSwitch peer memory, one process per GPU.  They stand where the
+ * reference would call nothing at all (it is single-process): sum over ranks of the k x d
+ * partials of dictionary.dot(X) / weights.T.dot(X) (archetypal_analysis.py:545-549,
+ * gpnh_convex_coding.py:219-224), of the k x k statistics (archetypal_analysis.py:541-556,
+ * gpnh_convex_coding.py:292-314), and the gathering of the k x T_local column blocks.
+ *
+ * Each rank allocates one symmetric region (same size everywhere), exports it, and imports
+ * the regions of the other ranks (the 64-byte handles travel through the host-side process
+ * group).  The first CDR_PEER_HEADER_BYTES of a region hold flags and counters and must not
+ * be used for data.  A buffer that takes part in a collective sits at the same byte offset in
+ * every region.  All ranks must issue the same sequence of collective calls with the same
+ * sizes.  STATUS: opt-in (CDR_PEER_COLLECTIVES=1); see DESIGN.md section 7.
+ */
+#define CDR_MAX_PEERS 8
+#define CDR_PEER_HEADER_BYTES (1u << 20)
+#define CDR_PEER_MAX_CTAS 256    /* grid limit of the collective kernels */
+#define CDR_PEER_MAX_STRIPS 2048 /* strips of the fused reduce-over-samples kernel */
+
+typedef struct cdr_peer_group {
+    int world;
+    int rank;
+    void* region[CDR_MAX_PEERS]; /* region[rank] is the local allocation */
+    size_t region_bytes;
+    size_t inbox_offset;         /* world slots of inbox_slot_bytes: push area of the fused kernel */
+    size_t inbox_slot_bytes;
+} cdr_peer_group;
+
+int cdr_peer_region_alloc(size_t bytes, void** region);  /* cudaMalloc + clear */
+int cdr_peer_region_free(void* region);
+int cdr_peer_export(void* region, unsigned char handle[64]);
+int cdr_peer_import(const unsigned char handle[64], void** region);
+int cdr_peer_release(void* imported_region);
+/* synchronising read (and clear) of the local time-out indicator: 0 = no wait timed out */
+int cdr_peer_error(const cdr_peer_group* group, int* error_out, cdr_stream_t stream);
+
+/* In-place sum over ranks of the n doubles at `offset` of every region (n even, offset a
+ * multiple of 16).  Two-shot: chunk c is summed in rank order by rank c % world, which
+ * pulls the peers' partials and pushes the sum to every rank. */
+int cdr_peer_allreduce(const cdr_peer_group* group, size_t offset, size_t n,
+                       const cdr_flags* flags, cdr_stream_t stream);
+
+/* Every rank pushes its k x ncols block (src: local device pointer, leading dimension lds)
+ * into columns [col0, col0 + ncols) of the k x ldd matrix at dst_offset of every region.
+ * max_cols = the largest ncols of any rank (sizes the grid identically everywhere). */
+int cdr_peer_allgather_columns(const cdr_peer_group* group, const double* src, long lds,
+                               size_t dst_offset, long ldd, int k, int col0, int ncols,
+                               int max_cols, const cdr_flags* flags, cdr_stream_t stream);
+
+/* cdr_reduce_samples fused with the sum over ranks: out (k x ldo, at out_offset of every
+ * region) = sum_r E (L_r X_r).  Each CTA pushes the tile of its feature strip straight from
+ * the epilogue into the inbox of the strip's owner rank, which sums the world tiles in rank
+ * order and pushes the result into `out` of every rank; the kernel ends when the local `out`
+ * is complete.  T_min = the smallest local T of any rank (keeps the kernel choice identical
+ * on all ranks).  Returns CDR_ERR_NOT_APPLICABLE for shapes the strip kernel does not cover
+ * (then: cdr_reduce_samples followed by cdr_peer_allreduce). */
+int cdr_reduce_samples_allreduce(const cdr_peer_group* group, const double* Lp, long sLi,
+                                 long sLt, const double* X, long ldx, int T, int T_min, int d,
+                                 int k, const double* E, size_t out_offset, long ldo,
+                                 const cdr_flags* flags, cdr_stream_t stream);
 
 #ifdef __cplusplus
 }

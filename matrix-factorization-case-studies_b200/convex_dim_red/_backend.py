@@ -79,6 +79,18 @@ class AaBuffers(ctypes.Structure):
                 ('grad_scale', ctypes.c_double), ('cost_scale', ctypes.c_double)]
 
 
+MAX_PEERS = 8
+PEER_HEADER_BYTES = 1 << 20
+
+
+class PeerGroupStruct(ctypes.Structure):
+    """Mirror of ``cdr_peer_group``."""
+
+    _fields_ = [('world', ctypes.c_int), ('rank', ctypes.c_int),
+                ('region', ctypes.c_void_p * MAX_PEERS), ('region_bytes', ctypes.c_size_t),
+                ('inbox_offset', ctypes.c_size_t), ('inbox_slot_bytes', ctypes.c_size_t)]
+
+
 # name -> (restype, argtypes); used both to bind and by the CPU-side symbol test
 _vp, _i, _l, _d, _sz = (ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_double,
                         ctypes.c_size_t)
@@ -125,6 +137,17 @@ SIGNATURES = {
     'cdr_row_sqnorms': (_i, [_vp, _l, _i, _i, _vp, _vp]),
     'cdr_column_moments': (_i, [_vp, _l, _i, _i, _vp, _vp, _vp]),
     'cdr_center_columns': (_i, [_vp, _l, _i, _i, _vp, _d, _vp]),
+    'cdr_peer_region_alloc': (_i, [_sz, ctypes.POINTER(ctypes.c_void_p)]),
+    'cdr_peer_region_free': (_i, [_vp]),
+    'cdr_peer_export': (_i, [_vp, ctypes.c_char_p]),
+    'cdr_peer_import': (_i, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
+    'cdr_peer_release': (_i, [_vp]),
+    'cdr_peer_error': (_i, [ctypes.POINTER(PeerGroupStruct), ctypes.POINTER(ctypes.c_int), _vp]),
+    'cdr_peer_allreduce': (_i, [ctypes.POINTER(PeerGroupStruct), _sz, _sz, _vp, _vp]),
+    'cdr_peer_allgather_columns': (_i, [ctypes.POINTER(PeerGroupStruct), _vp, _l, _sz, _l, _i,
+                                        _i, _i, _i, _vp, _vp]),
+    'cdr_reduce_samples_allreduce': (_i, [ctypes.POINTER(PeerGroupStruct), _vp, _l, _l, _vp, _l,
+                                          _i, _i, _i, _i, _vp, _sz, _l, _vp, _vp]),
 }
 
 _LIB = None
@@ -148,7 +171,9 @@ def library():
     return _LIB
 
 
-_ERRORS = {-1: 'invalid argument', -2: 'unsupported configuration', -3: 'workspace too small'}
+_ERRORS = {-1: 'invalid argument', -2: 'unsupported configuration', -3: 'workspace too small',
+           -4: 'shape not covered by the fused kernel'}
+ERR_NOT_APPLICABLE = -4
 
 
 def check(rc, what):

@@ -40,10 +40,57 @@ class Comm:
         self.group = group
         self.world = dist.get_world_size(group) if self.enabled else 1
         self.rank = dist.get_rank(group) if self.enabled else 0
+        self.peer = None          # _peer.PeerGroup once setup_peer() has run ...
+        self.peer_on = False      # ... and whether the current fit uses it
+
+    # -- peer-memory collectives (opt-in, CDR_PEER_COLLECTIVES=1) ---------------------------
+    def setup_peer(self, shapes, inbox_shape):
+        """Prepare the symmetric region for the fp64 tensors ``shapes`` (allocated afterwards,
+        in this order, with :meth:`zeros`) and a per-rank inbox slot of ``inbox_shape``.
+        Collective: every rank calls it with the same arguments.  Returns the PeerGroup, or
+        None when peer collectives are off (then :meth:`zeros` gives ordinary tensors and the
+        collectives go through ``torch.distributed``)."""
+        from . import _peer
+        self.peer_on = self.enabled and _peer.peer_collectives_enabled()
+        if not self.peer_on:
+            return None
+        count = lambda shape: int(np.prod(shape))
+        data_bytes = sum(_peer.round_up(count(s) * 8 + 8) for s in shapes)
+        slot_bytes = count(inbox_shape) * 8
+        if self.peer is not None and not self.peer.fits(data_bytes, slot_bytes):
+            self.peer.close()
+            self.peer = None
+        if self.peer is None:
+            self.peer = _peer.PeerGroup(self, data_bytes, slot_bytes)
+        else:
+            self.peer.reset()
+        return self.peer
+
+    def close_peer(self):
+        """Unmap and free the symmetric regions (collective)."""
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
+        self.peer_on = False
+
+    def zeros(self, *shape):
+        """fp64 zeros on the device: inside the symmetric region when peer collectives are
+        set up (so the tensor can take part in them), an ordinary tensor otherwise."""
+        if self.peer_on:
+            return self.peer.zeros(*shape)
+        from . import _backend as be
+        return be.zeros(*shape)
+
+    def _peer_tensor(self, t):
+        import torch
+        return (self.peer_on and t.is_cuda and t.dtype == torch.float64 and
+                self.peer.contains(t))
 
     def allreduce_sum(self, t):
         """In-place sum over ranks (a no-op without a group)."""
         if self.enabled:
+            if self._peer_tensor(t) and self.peer.can_allreduce(t):
+                return self.peer.allreduce(t)
             self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
         return t
 
@@ -64,6 +111,8 @@ class Comm:
         if not self.enabled:
             out[:, :sizes[0]].copy_(local[:, :sizes[0]])
             return out
+        if self._peer_tensor(out):
+            return self.peer.allgather_columns(local, out, sizes)
         nmax = max(sizes)
         if scratch is None:
             scratch = torch.zeros((self.world + 1, k, nmax), dtype=local.dtype,

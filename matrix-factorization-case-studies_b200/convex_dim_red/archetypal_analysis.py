@@ -107,17 +107,23 @@ class _AaEngine:
         self.alpha = be.to_device(np.asarray(alpha, dtype=np.float64))
         self.G = be.zeros(k, ldt)
         self.D = be.zeros(k, ldt)
-        self.CK = be.zeros(k, ldt)
-        self.DK = be.zeros(k, ldt)
-        self.KZt = be.zeros(k, ldt)
-        self.ZtZ = be.zeros(k, k)
+        # buffers that are summed / gathered over ranks live in the symmetric peer region when
+        # the peer-memory collectives are on (CDR_PEER_COLLECTIVES=1); plain tensors otherwise
+        self.peer = None
+        if mode == 'feature':
+            self.peer = self.comm.setup_peer(
+                [(k, ldt), (k, ldt), (k, ldt), (k, k), (k, self.ldx)], (k, self.ldx))
+        self.CK = self.comm.zeros(k, ldt)
+        self.DK = self.comm.zeros(k, ldt)
+        self.KZt = self.comm.zeros(k, ldt)
+        self.ZtZ = self.comm.zeros(k, k)
         self.CKCt = be.zeros(k, k)
         self.CKZ = be.zeros(k, k)
         self.G01 = be.zeros(k, k)
         self.G11 = be.zeros(k, k)
         self.row_scratch = be.zeros(8 * k)
         if mode == 'feature':
-            self.tmp_kd = be.zeros(k, self.ldx)
+            self.tmp_kd = self.comm.zeros(k, self.ldx)
         else:
             self.Zt = be.zeros(k, ldt)
         if self.comm.enabled:
@@ -149,32 +155,40 @@ class _AaEngine:
         self._first_dictionary_update = True
 
     # -- products with K ----------------------------------------------------
+    def _samples_sum(self, L, sLi, sLt, flags):
+        """tmp_kd = sum over ranks of L_r X_r (k x d): one kernel over peer memory where the
+        strip kernel applies, else the local pass followed by an all-reduce."""
+        Tl, d, k = self.Tl, self.d, self.k
+        if self.peer is not None and self.peer.reduce_samples_allreduce(
+                L, sLi, sLt, self.X, Tl, min(self.sizes), d, k, self.tmp_kd, flags=flags):
+            return
+        be.reduce_samples(L, sLi, sLt, self.X, Tl, d, k, self.tmp_kd, self.ws, flags=flags)
+        self.comm.allreduce_sum(self.tmp_kd)
+
     def _features_to_columns(self, out, flags):
         """(tmp_kd) X' for this rank's samples, placed in (all-gathered into) `out`."""
         Tl, d, k = self.Tl, self.d, self.k
         if not self.comm.enabled:
             be.reduce_features(self.tmp_kd, self.X, Tl, d, k, out, self.ws, flags)
             return
-        self.comm.allreduce_sum(self.tmp_kd)
         be.reduce_features(self.tmp_kd, self.X, Tl, d, k, self.loc_kt, self.ws, flags)
         self.comm.allgather_columns(self.loc_kt, out, self.sizes, self.gather_scratch)
 
     def apply_left(self, L, out, flags):
         """out = L K for a k x T matrix L (dictionary.dot(K) or (L X) X')."""
-        Tl, d, k = self.Tl, self.d, self.k
+        Tl, k = self.Tl, self.k
         if self.mode == 'feature':
             Lloc = L[:, self.lo:] if self.lo else L
-            be.reduce_samples(Lloc, L.stride(0), 1, self.X, Tl, d, k, self.tmp_kd, self.ws,
-                              flags=flags)
+            self._samples_sum(Lloc, L.stride(0), 1, flags)
             self._features_to_columns(out, flags)
         else:
             be.reduce_samples(L, L.stride(0), 1, self.X, Tl, Tl, k, out, self.ws, flags=flags)
 
     def apply_right(self, flags):
         """KZt = (K Z)' (K.dot(weights) or X (X' Z))."""
-        Tl, d, k = self.Tl, self.d, self.k
+        Tl, k = self.Tl, self.k
         if self.mode == 'feature':
-            be.reduce_samples(self.Z, 1, k, self.X, Tl, d, k, self.tmp_kd, self.ws, flags=flags)
+            self._samples_sum(self.Z, 1, k, flags)
             self._features_to_columns(self.KZt, flags)
         else:
             self.Zt[:, :Tl].copy_(self.Z.t())
@@ -354,6 +368,8 @@ class _AaEngine:
         torch.cuda.synchronize()
         elapsed = time.perf_counter() - start
         st = self.state.read()
+        if self.peer is not None:
+            self.peer.check()          # a wait inside a peer collective timed out
         be.trace('aa: remaining iterations')
         if st.error_stage:
             raise RuntimeError('factorization cost increased after {} update'.format(

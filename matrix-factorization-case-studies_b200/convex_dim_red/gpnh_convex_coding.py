@@ -65,11 +65,15 @@ class _GpnhEngine:
         self.ldx = self.X.stride(0)
         self.ldt = be.round_up(T)
         self.Z = be.to_device(weights)
-        self.WT = be.to_device_padded(np.ascontiguousarray(np.asarray(dictionary).T))
+        # buffers that are summed over ranks live in the symmetric peer region when the
+        # peer-memory collectives are on (CDR_PEER_COLLECTIVES=1); plain tensors otherwise
+        self.peer = self.comm.setup_peer([(k, self.ldx), (3, k, k)], (k, self.ldx))
+        self.WT = self.comm.zeros(k, self.ldx)
+        self.WT[:, :d].copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(dictionary).T)))
         self.XWt = be.zeros(k, self.ldt)
         # the statistics that reduce over samples share one buffer (one all-reduce):
         # Z'Z, (X W)'Z and -- sharded fits only -- the (X W)'Z of the dictionary sub-step
-        self.stats = be.zeros(3, k, k)
+        self.stats = self.comm.zeros(3, k, k)
         self.ZtZ = self.stats[0]
         self.XWtZ = self.stats[1]
         self.XWtZ_dict = self.stats[2]
@@ -89,6 +93,9 @@ class _GpnhEngine:
         n_tot = torch.tensor([T], dtype=torch.int64, device='cuda')
         self.comm.allreduce_sum(n_tot)
         self.T_total = int(n_tot.item())
+        t_min = torch.tensor([-T], dtype=torch.int64, device='cuda')
+        self.comm.allreduce_max(t_min)
+        self.T_min = -int(t_min.item())      # smallest local T: keeps kernel choices identical
         self.lib = be.library()
 
     # -- small products -----------------------------------------------------
@@ -137,8 +144,12 @@ class _GpnhEngine:
         be.check(self.lib.cdr_gpnh_solve_matrix(
             self.ZtZ.data_ptr(), k, self.T_total, d, self.lambda_W, self.P.data_ptr(), None, 0,
             fl, be.stream_ptr()), 'cdr_gpnh_solve_matrix')
-        be.reduce_samples(self.Z, 1, k, self.X, T, d, k, self.WT, self.ws, E=self.P, flags=fl)
-        self.comm.allreduce_sum(self.WT)          # W' = P sum_g Z_g' X_g
+        # W' = P sum_g Z_g' X_g: one kernel over peer memory where the strip kernel applies,
+        # else the local pass followed by an all-reduce
+        if self.peer is None or not self.peer.reduce_samples_allreduce(
+                self.Z, 1, k, self.X, T, self.T_min, d, k, self.WT, E=self.P, flags=fl):
+            be.reduce_samples(self.Z, 1, k, self.X, T, d, k, self.WT, self.ws, E=self.P, flags=fl)
+            self.comm.allreduce_sum(self.WT)
         be.reduce_features(self.WT, self.X, T, d, k, self.XWt, self.ws, fl)
         descs = [self._desc_WtW(), self._desc_XWtZ()]
         if self.lambda_W != 0:
@@ -224,6 +235,8 @@ class _GpnhEngine:
         torch.cuda.synchronize()
         elapsed = time.perf_counter() - start
         st = self.state.read()
+        if self.peer is not None:
+            self.peer.check()          # a wait inside a peer collective timed out
         be.trace('gpnh: remaining iterations')
         if st.error_stage:
             raise RuntimeError('factorization cost increased after {} update'.format(

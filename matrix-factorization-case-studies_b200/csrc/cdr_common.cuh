@@ -154,5 +154,9 @@ int run_reduce_features_tma(const double* M, long ldm, const double* X, long ldx
                             const cdr_flags* flags, cudaStream_t stream);
 size_t reduce_features_tma_workspace_bytes(int T, int d, int k);
 void tma_stream_plan(int T, int d, int k, int with_epilogue, int* out);
+int run_reduce_samples_exchange(const cdr_peer_group& g, size_t out_offset, const double* Lp,
+                                long sLi, long sLt, const double* X, long ldx, int T, int T_min,
+                                int d, int k, const double* E, long ldo, const cdr_flags* flags,
+                                cudaStream_t stream);
 
 }  // namespace cdr

@@ -15,11 +15,16 @@
 //                          the four feature quarters are combined through shared
 //                          memory and written as per-strip partials (a few % of the
 //                          bytes of X), summed in fixed order by a finalize kernel.
+#include <type_traits>
+
 #include "stream_tma.cuh"
+#include "peer.cuh"
 
 namespace cdr {
 
 using namespace tma;
+using peer::NoExchange;
+using peer::SamplesExchange;
 
 // ======================================================================
 // reduce over samples (strip owned)
@@ -30,15 +35,27 @@ using namespace tma;
 constexpr int kSampTR = 16;
 constexpr int kSampKS = kSampTR / 4;
 
-template <int KT, int MAXU, bool FUSE_E>
+// barrier over the eight consumer warps only (the producer warp runs ahead / has exited)
+__device__ __forceinline__ void samples_consumer_barrier()
+{
+    asm volatile("bar.sync 2, %0;\n" ::"n"(kConsumerWarps * 32) : "memory");
+}
+
+// Exchange = NoExchange: `out` is the local result.
+// Exchange = SamplesExchange (sample-sharded fit): the strip's tile is pushed into the inbox
+// of the strip's owner rank (strip % world) instead; the owner sums the world tiles in rank
+// order and pushes the sum into `out` of every rank (peer.cuh describes the flags).
+template <int KT, int MAXU, bool FUSE_E, class Exchange = NoExchange>
 __global__ void __launch_bounds__(kThreads, 1)
 reduce_samples_tma_kernel(const double* __restrict__ Lp, long sLi, long sLt,
                           const double* __restrict__ X, long ldx, int T, int dpad, int k, int TC,
                           int nstrips, int stages, const double* __restrict__ E,
-                          double* __restrict__ out, long ldo, const cdr_flags* flags)
+                          double* __restrict__ out, long ldo, const cdr_flags* flags,
+                          Exchange xch = Exchange())
 {
     if (is_done(flags)) return;
     constexpr int KP = 8 * KT;
+    constexpr bool kExchange = !std::is_same<Exchange, NoExchange>::value;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
     double* Es = reinterpret_cast<double*>(smem_raw + 128);
@@ -89,11 +106,20 @@ reduce_samples_tma_kernel(const double* __restrict__ Lp, long sLi, long sLt,
 
     // ---------------------------------- consumers
     const int lr = lane & 3, lc = lane >> 2;
+    unsigned long long epoch = 0;
+    if constexpr (kExchange)
+        epoch = peer::header_of(xch.g, xch.g.rank)->fused_seq[blockIdx.x] + 1;
     int it = 0;
     for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
         const int c0 = strip * TC;
         const int w = min(TC, dpad - c0);
         const int nunits = w / 16;
+        if constexpr (kExchange) {
+            // this rank's slot in the inbox of the strip's owner takes the place of `out`
+            const cdr_peer_group& g = xch.g;
+            out = reinterpret_cast<double*>(static_cast<unsigned char*>(g.region[strip % g.world]) +
+                                            g.inbox_offset + (size_t)g.rank * g.inbox_slot_bytes);
+        }
 
         double acc[MAXU][KT][2][2];
 #pragma unroll
@@ -198,6 +224,63 @@ reduce_samples_tma_kernel(const double* __restrict__ Lp, long sLi, long sLt,
                 __syncwarp();
             }
         }
+
+        if constexpr (kExchange) {
+            const cdr_peer_group& g = xch.g;
+            const int owner = strip % g.world;
+            peer::PeerHeader* mine = peer::header_of(g, g.rank);
+            __threadfence_system();
+            samples_consumer_barrier();                       // the whole tile has been pushed
+            if (threadIdx.x == 0)
+                peer::st_release_sys(&peer::header_of(g, owner)->ready[strip][g.rank], epoch);
+            if (owner == g.rank) {
+                if ((int)threadIdx.x < g.world)
+                    peer::wait_flag(&mine->ready[strip][threadIdx.x], epoch, mine, peer::kWaitReady);
+                samples_consumer_barrier();                   // every rank's tile of this strip is here
+                const unsigned char* inbox =
+                    static_cast<const unsigned char*>(g.region[g.rank]) + g.inbox_offset;
+                const int w2 = w / 2;
+                for (int idx = threadIdx.x; idx < k * w2; idx += kConsumerWarps * 32) {
+                    const int i = idx / w2, c = (idx - i * w2) * 2;
+                    const size_t el = (size_t)i * ldo + c0 + c;
+                    double2 part[CDR_MAX_PEERS];
+#pragma unroll
+                    for (int r = 0; r < CDR_MAX_PEERS; ++r)
+                        if (r < g.world)
+                            part[r] = peer::ld_sys_d2(reinterpret_cast<const double*>(
+                                          inbox + (size_t)r * g.inbox_slot_bytes) + el);
+                    double2 sum = part[0];
+#pragma unroll
+                    for (int r = 1; r < CDR_MAX_PEERS; ++r)
+                        if (r < g.world) {
+                            sum.x += part[r].x;
+                            sum.y += part[r].y;
+                        }
+#pragma unroll
+                    for (int r = 0; r < CDR_MAX_PEERS; ++r)
+                        if (r < g.world)
+                            *reinterpret_cast<double2*>(
+                                reinterpret_cast<double*>(static_cast<unsigned char*>(g.region[r]) +
+                                                          xch.out_offset) + el) = sum;
+                }
+                __threadfence_system();
+                samples_consumer_barrier();                   // the sum has been pushed to every rank
+                if ((int)threadIdx.x < g.world)
+                    peer::st_release_sys(&peer::header_of(g, threadIdx.x)->done[strip], epoch);
+            }
+        }
+    }
+
+    if constexpr (kExchange) {
+        // the local `out` is complete once the owners of all strips of this CTA said so; this
+        // also keeps a fast rank from pushing the next launch's tiles into an inbox slot whose
+        // owner has not consumed the current ones
+        peer::PeerHeader* mine = peer::header_of(xch.g, xch.g.rank);
+        for (int strip = blockIdx.x + (int)threadIdx.x * (int)gridDim.x; strip < nstrips;
+             strip += kConsumerWarps * 32 * (int)gridDim.x)
+            peer::wait_flag(&mine->done[strip], epoch, mine, peer::kWaitDone);
+        samples_consumer_barrier();
+        if (threadIdx.x == 0) mine->fused_seq[blockIdx.x] = epoch;
     }
 }
 
@@ -508,6 +591,59 @@ int run_reduce_samples_tma(const double* Lp, long sLi, long sLt, const double* X
     if (kt == 3) CDR_S(3, 2);
     CDR_S(4, 2);
 #undef CDR_S
+}
+
+// Fused with the sum over ranks (cdr_reduce_samples_allreduce).  The plan uses the smallest
+// local T of any rank, so every rank takes the same decision and the same grid.
+template <int KT, int MAXU, bool FUSE_E>
+static int launch_samples_exchange(const cdr_peer_group& g, size_t out_offset, const double* Lp,
+                                   long sLi, long sLt, const double* X, long ldx, int T, int dpad,
+                                   int k, int TC, int nstrips, const double* E, long ldo,
+                                   const cdr_flags* flags, cudaStream_t stream)
+{
+    constexpr int KP = 8 * KT;
+    const size_t fixed = samples_fixed_smem(KP, FUSE_E);
+    const size_t stage = (size_t)kSampTR * (TC + 4) * 8;
+    const int stages = ring_stages(fixed, stage);
+    if (stages < 2) return CDR_ERR_NOT_APPLICABLE;
+    const size_t smem = fixed + stages * stage;
+    int rc = ensure_smem<reduce_samples_tma_kernel<KT, MAXU, FUSE_E, SamplesExchange>>(smem);
+    if (rc) return rc;
+    const int grid = nstrips < sm_count() ? nstrips : sm_count();
+    if (grid > CDR_PEER_MAX_CTAS || nstrips > CDR_PEER_MAX_STRIPS) return CDR_ERR_NOT_APPLICABLE;
+    SamplesExchange xch;
+    xch.g = g;
+    xch.out_offset = out_offset;
+    reduce_samples_tma_kernel<KT, MAXU, FUSE_E, SamplesExchange><<<grid, kThreads, smem, stream>>>(
+        Lp, sLi, sLt, X, ldx, T, dpad, k, TC, nstrips, stages, E, nullptr, ldo, flags, xch);
+    CDR_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+int run_reduce_samples_exchange(const cdr_peer_group& g, size_t out_offset, const double* Lp,
+                                long sLi, long sLt, const double* X, long ldx, int T, int T_min,
+                                int d, int k, const double* E, long ldo, const cdr_flags* flags,
+                                cudaStream_t stream)
+{
+    if (tma_disabled() || k > 16) return CDR_ERR_NOT_APPLICABLE;
+    if ((ldx % 2) != 0 || (((uintptr_t)X) & 15) != 0) return CDR_ERR_NOT_APPLICABLE;
+    const int dpad = (d + 31) / 32 * 32;
+    int TC, nstrips;
+    if (!samples_strip_plan(T_min, dpad, k, E != nullptr, &TC, &nstrips))
+        return CDR_ERR_NOT_APPLICABLE;
+#define CDR_SX(KT)                                                                               \
+    do {                                                                                         \
+        if (E != nullptr)                                                                        \
+            return launch_samples_exchange<KT, 4, true>(g, out_offset, Lp, sLi, sLt, X, ldx, T,  \
+                                                        dpad, k, TC, nstrips, E, ldo, flags,     \
+                                                        stream);                                 \
+        return launch_samples_exchange<KT, 4, false>(g, out_offset, Lp, sLi, sLt, X, ldx, T,     \
+                                                     dpad, k, TC, nstrips, nullptr, ldo, flags,  \
+                                                     stream);                                    \
+    } while (0)
+    if (k <= 8) CDR_SX(1);
+    CDR_SX(2);
+#undef CDR_SX
 }
 
 constexpr int kFsTcMax = 384;

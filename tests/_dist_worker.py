@@ -260,6 +260,121 @@ def run_nccl(out):
     dist.destroy_process_group()
 
 
+def run_peer(out):
+    """Peer-memory collectives (CDR_PEER_COLLECTIVES=1) against NCCL / the unfused kernels."""
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    os.environ['CDR_PEER_COLLECTIVES'] = '1'
+    from convex_dim_red import _backend as be
+    from convex_dim_red._dist import Comm, shard_bounds, shard_sizes
+    from convex_dim_red import archetypal_analysis as aa
+    from convex_dim_red import gpnh_convex_coding as gp
+    comm = Comm()
+    rank, world = comm.rank, comm.world
+    report = {}
+
+    # --- stand-alone collectives on tensors of several sizes (odd, tiny, multi-chunk, 2.8 MB)
+    T, d, k = 1620 // world, 44000, 8
+    ldx = be.round_up(d)
+    shapes = [(3, 5, 5), (2,), (k, k), (4100,), (k, ldx), (k, be.round_up(203))]
+    peer = comm.setup_peer(shapes + [(k, ldx)], (k, ldx))
+    assert peer is not None
+    gen = torch.Generator(device='cuda').manual_seed(100 + rank)
+    tensors = [comm.zeros(*shape) for shape in shapes[:5]]
+    for rep in range(3):                                   # several epochs of every flag
+        for i, t in enumerate(tensors):
+            t.copy_(torch.randn(t.shape, generator=gen, device='cuda', dtype=torch.float64))
+            want = t.clone()
+            dist.all_reduce(want)
+            assert peer.can_allreduce(t)
+            comm.allreduce_sum(t)
+            torch.cuda.synchronize()
+            exact = bool(torch.equal(t, want))
+            close = bool(torch.allclose(t, want, rtol=1e-13, atol=1e-13))
+            report['allreduce_%d_%d' % (rep, i)] = (exact if world == 2 else close)
+    # views: an even-length prefix goes through the peer kernel, an odd-length middle view
+    # falls back to NCCL -- both must give the right sum
+    stats = tensors[0]
+    stats.copy_(torch.randn(stats.shape, generator=gen, device='cuda', dtype=torch.float64))
+    want = stats.clone()
+    dist.all_reduce(want)
+    assert peer.can_allreduce(stats[:2]) and not peer.can_allreduce(stats[1])
+    comm.allreduce_sum(stats[:2])
+    comm.allreduce_sum(stats[2])
+    torch.cuda.synchronize()
+    report['allreduce_views'] = bool(torch.allclose(stats, want, rtol=1e-13, atol=1e-13))
+
+    # --- all-gather of ragged column blocks
+    sizes = shard_sizes(203, world)
+    outk = comm.zeros(k, be.round_up(203))
+    local = torch.randn((k, be.round_up(sizes[rank])), generator=gen, device='cuda',
+                        dtype=torch.float64)
+    comm.allgather_columns(local, outk, sizes)
+    torch.cuda.synchronize()
+    parts = comm.allgather_objects(local[:, :sizes[rank]].cpu())
+    report['allgather'] = bool(torch.equal(outk[:, :203].cpu(), torch.cat(parts, dim=1)))
+
+    # --- fused reduce-over-samples + all-reduce against the unfused pair
+    Xl = torch.randn((T, ldx), generator=gen, device='cuda', dtype=torch.float64)
+    Xl[:, d:] = 0
+    Z = torch.rand((T, k), generator=gen, device='cuda', dtype=torch.float64)
+    E = torch.randn((k, k), generator=gen, device='cuda', dtype=torch.float64)
+    fused = tensors[4]
+    ws = be.Workspace(T, d, k)
+    for name, Em in (('plain', None), ('epilogue', E)):
+        ref = be.zeros(k, ldx)
+        be.reduce_samples(Z, 1, k, Xl, T, d, k, ref, ws, E=Em)
+        dist.all_reduce(ref)
+        for rep in range(3):
+            fused.zero_()
+            ok = peer.reduce_samples_allreduce(Z, 1, k, Xl, T, T, d, k, fused, E=Em)
+            torch.cuda.synchronize()
+            report['fused_%s_%d' % (name, rep)] = bool(ok) and (
+                bool(torch.equal(fused, ref)) if world == 2 else
+                bool(torch.allclose(fused, ref, rtol=1e-13, atol=1e-12)))
+    peer.check()
+
+    # --- the sharded engines with peer collectives against the same engines over NCCL
+    X, Z0, W0, C0 = problem(T=403, d=2600, k=8, path=DATA[0])       # direct-load kernels
+    lo, hi = shard_bounds(X.shape[0], world, rank)
+    big = np.random.RandomState(3).randn(1300, 44000) * 0.1          # strip kernels (fused path)
+    blo, bhi = shard_bounds(big.shape[0], world, rank)
+    bZ = np.random.RandomState(4).rand(1300, 8)
+    bZ /= bZ.sum(axis=1, keepdims=True)
+    bW = 0.1 * np.random.RandomState(5).randn(44000, 8)
+    bC = np.random.RandomState(6).rand(8, 1300)
+    bC /= bC.sum(axis=1, keepdims=True)
+    results = {}
+    for mode in ('1', '0'):
+        os.environ['CDR_PEER_COLLECTIVES'] = mode
+        g = gp._iterate_gpnh_convex_coding(X[lo:hi].copy(), Z0[lo:hi].copy(), W0.copy(),
+                                           lambda_W=0.2, tolerance=1e-12, max_iterations=6,
+                                           comm=comm)
+        a = aa._iterate_aa(X[lo:hi].copy(), Z0[lo:hi].copy(), C0.copy(), np.ones(8),
+                           tolerance=1e-12, max_iterations=6,
+                           dictionary_solver_kwargs=dict(max_iterations=2), comm=comm)
+        gb = gp._iterate_gpnh_convex_coding(big[blo:bhi].copy(), bZ[blo:bhi].copy(), bW.copy(),
+                                            tolerance=1e-12, max_iterations=12, comm=comm)
+        ab = aa._iterate_aa(big[blo:bhi].copy(), bZ[blo:bhi].copy(), bC.copy(), np.ones(8),
+                            tolerance=1e-12, max_iterations=8,
+                            dictionary_solver_kwargs=dict(max_iterations=1), comm=comm)
+        results[mode] = (g, a, gb, ab)
+    for idx, name in enumerate(('gpnh_small', 'aa_small', 'gpnh_strip', 'aa_strip')):
+        p, n = results['1'][idx], results['0'][idx]
+        cost_p, cost_n = (p[2], n[2]) if name.startswith('gpnh') else (p[3], n[3])
+        report['engine_%s_cost' % name] = bool(np.isclose(cost_p, cost_n, rtol=1e-10, atol=0))
+        report['engine_%s_Z' % name] = bool(np.allclose(p[0], n[0], rtol=0, atol=1e-7))
+        report['engine_%s_D' % name] = bool(np.allclose(p[1], n[1], rtol=0, atol=1e-7))
+    comm.close_peer()
+    reports = comm.allgather_objects(report)
+    if rank == 0:
+        bad = sorted({key for rep in reports for key, ok in rep.items() if not ok})
+        np.savez(out, n_checks=np.array([len(report)]), failed=np.array(bad, dtype=str))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('--mode', required=True)
@@ -267,4 +382,4 @@ if __name__ == '__main__':
     ap.add_argument('--data', default=None)
     args = ap.parse_args()
     DATA[0] = args.data
-    (run_gloo if args.mode == 'gloo' else run_nccl)(args.out)
+    {'gloo': run_gloo, 'nccl': run_nccl, 'peer': run_peer}[args.mode](args.out)

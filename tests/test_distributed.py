@@ -104,3 +104,26 @@ def test_sharded_engines_nccl_world2(tmp_path):
         check('k_%s_inertia' % name, lambda name=name: np.testing.assert_allclose(
             got['k_%s_inertia' % name], want['k_%s_inertia' % name], rtol=1e-10))
     assert not problems, '\n'.join(problems)
+
+
+@pytest.mark.gpu
+def test_peer_collectives_world2(tmp_path):
+    """Peer-memory collectives (include/cdr_b200.h, cdr_peer_*) on two GPUs: stand-alone
+    all-reduce / all-gather against NCCL, the fused reduce-over-samples + all-reduce against
+    the unfused pair (bit-identical for two ranks), and the sharded engines with
+    CDR_PEER_COLLECTIVES=1 against the same engines over NCCL.  Opt-in while the path is
+    opt-in: set CDR_TEST_PEER=1."""
+    torch = pytest.importorskip('torch')
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    if os.environ.get('CDR_TEST_PEER', '0') != '1':
+        pytest.skip('peer collectives are opt-in (CDR_TEST_PEER=1)')
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from _dist_worker import problem
+    out = str(tmp_path / 'peer.npz')
+    data = str(tmp_path / 'problem.npz')
+    problem(T=403, d=2600, k=8, path=data)
+    _launch('peer', out, data=data, timeout=300)
+    got = np.load(out)
+    assert int(got['n_checks'][0]) > 30
+    assert list(got['failed']) == []

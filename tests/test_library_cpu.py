@@ -48,17 +48,62 @@ def test_struct_layouts_match_the_header(tmp_path):
     from convex_dim_red import _backend as be
     src = tmp_path / 'sizes.c'
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "cdr_b200.h"\n'
-                   'int main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(cdr_spg_params),'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %d %u\\n", '
+                   'sizeof(cdr_spg_params),'
                    'sizeof(cdr_loop_state), sizeof(cdr_small_gram_desc), sizeof(cdr_aa_buffers),'
-                   'offsetof(cdr_loop_state, tolerance), offsetof(cdr_aa_buffers, grad_scale));'
+                   'offsetof(cdr_loop_state, tolerance), offsetof(cdr_aa_buffers, grad_scale),'
+                   'sizeof(cdr_peer_group), offsetof(cdr_peer_group, inbox_offset),'
+                   'CDR_MAX_PEERS, CDR_PEER_HEADER_BYTES);'
                    'return 0;}\n')
     exe = tmp_path / 'sizes'
     subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     want = [ctypes.sizeof(be.SpgParams), ctypes.sizeof(be.LoopState),
             ctypes.sizeof(be.SmallGramDesc), ctypes.sizeof(be.AaBuffers),
-            be.LoopState.tolerance.offset, be.AaBuffers.grad_scale.offset]
+            be.LoopState.tolerance.offset, be.AaBuffers.grad_scale.offset,
+            ctypes.sizeof(be.PeerGroupStruct), be.PeerGroupStruct.inbox_offset.offset,
+            be.MAX_PEERS, be.PEER_HEADER_BYTES]
     assert got == want
+
+
+def test_peer_collective_host_logic(lib):
+    """Region layout, argument validation and the eligibility rules of the peer all-reduce,
+    without a GPU (no kernel is launched: every call below is rejected on its arguments)."""
+    from convex_dim_red import _backend as be, _peer
+    inbox, data, total = _peer.region_layout(8, 3 * 1000 + 5, 8 * 44000 * 8)
+    assert inbox == be.PEER_HEADER_BYTES and data == inbox + 8 * _peer.round_up(8 * 44000 * 8)
+    assert total == data + _peer.round_up(3005) and total % _peer.ALIGN == 0
+    assert not _peer.peer_collectives_enabled() or os.environ.get('CDR_PEER_COLLECTIVES') == '1'
+
+    g = be.PeerGroupStruct()
+    g.world, g.rank, g.region_bytes = 2, 0, 16 << 20
+    g.inbox_offset, g.inbox_slot_bytes = be.PEER_HEADER_BYTES, 1 << 20
+    ref = ctypes.byref(g)
+    assert lib.cdr_peer_allreduce(ref, be.PEER_HEADER_BYTES, 16, None, None) == -1   # no regions
+    g.region[0], g.region[1] = 0x1000, 0x2000            # never dereferenced: rejected earlier
+    assert lib.cdr_peer_allreduce(ref, be.PEER_HEADER_BYTES, 15, None, None) == -1   # odd count
+    assert lib.cdr_peer_allreduce(ref, 64, 16, None, None) == -1                     # in header
+    assert lib.cdr_peer_allreduce(ref, be.PEER_HEADER_BYTES + 8, 16, None, None) == -1
+    assert lib.cdr_peer_allreduce(ref, (16 << 20) - 64, 16, None, None) == -1        # overruns
+    g.world = 9
+    assert lib.cdr_peer_allreduce(ref, be.PEER_HEADER_BYTES, 16, None, None) == -1
+    g.world = 2
+    assert lib.cdr_peer_allgather_columns(ref, 0x3000, 10, 3 << 20, 4, 8, 0, 10, 10, None,
+                                          None) == -1                               # ldd < cols
+    # fused reduce + all-reduce: output must fit an inbox slot, shapes the strip kernel does
+    # not cover are reported as "not applicable" (the caller then runs the unfused pair)
+    out_off = 4 << 20
+    args = (None, 1, 8, 0x3000, 44000, 810, 810, 44000, 8, None)
+    assert lib.cdr_reduce_samples_allreduce(ref, *args, out_off, 44000, None, None) == \
+        be.ERR_NOT_APPLICABLE                                                        # slot too small
+    small = (None, 1, 8, 0x3000, 320, 100, 100, 300, 8, None)
+    assert lib.cdr_reduce_samples_allreduce(ref, *small, out_off, 320, None, None) == \
+        be.ERR_NOT_APPLICABLE                                                        # too few strips
+    assert lib.cdr_reduce_samples_allreduce(ref, *small, 8, 320, None, None) == -1   # offset in header
+    # on a machine without a CUDA device the allocation reports the CUDA error, it does not crash
+    base = ctypes.c_void_p()
+    rc = lib.cdr_peer_region_alloc(1 << 10, ctypes.byref(base))
+    assert rc == -1                                                                  # below header size
 
 
 def test_no_cpu_fallback_without_cuda():

@@ -10,10 +10,13 @@
 //   writer : data stores, __threadfence_system(), CTA barrier, st.release.sys flag = epoch
 //   reader : spin on ld.acquire.sys flag >= epoch, CTA barrier, ld.relaxed.sys data
 //
-// Epochs come from per-CTA launch counters kept in the region header: CTA b of launch n
-// uses epoch n on every rank, because all ranks issue the same sequence of collective
-// launches with the same grids (the replicated k x k / k x T state is bit-identical across
-// ranks, so even the device-side `done` early exit is taken by all ranks together).
+// Epochs come from launch counters kept in the region header, which advance identically on
+// every rank because all ranks issue the same sequence of collective launches with the same
+// grids (the replicated k x k / k x T state is bit-identical across ranks, so even the
+// device-side `done` early exit is taken by all ranks together).  The stand-alone collectives
+// index both their flags and their counters by CTA; the fused kernel indexes its flags by
+// strip, so it uses one counter per launch (bumped by the last CTA to leave), which stays
+// monotonic for every strip whatever grid a later launch uses.
 // Sums are formed by one owner per chunk in rank order 0..world-1 and pushed to every
 // rank, which keeps the replicas bit-identical and the result run-to-run deterministic.
 //
@@ -28,7 +31,9 @@ namespace peer {
 
 // The first CDR_PEER_HEADER_BYTES of every region.  Zero-initialised at allocation.
 struct PeerHeader {
-    unsigned long long fused_seq[CDR_PEER_MAX_CTAS];    // launches of the fused reduce kernel
+    unsigned long long fused_epoch;                      // completed launches of the fused kernel
+    unsigned int fused_tickets;                          // CTAs of the current launch that left
+    unsigned int reserved_;
     unsigned long long coll_seq[CDR_PEER_MAX_CTAS];     // launches of the stand-alone collectives
     unsigned long long coll_start[CDR_MAX_PEERS][CDR_PEER_MAX_CTAS];   // [from rank][cta]
     unsigned long long coll_finish[CDR_MAX_PEERS][CDR_PEER_MAX_CTAS];

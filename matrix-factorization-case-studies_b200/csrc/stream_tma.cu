@@ -108,7 +108,7 @@ reduce_samples_tma_kernel(const double* __restrict__ Lp, long sLi, long sLt,
     const int lr = lane & 3, lc = lane >> 2;
     unsigned long long epoch = 0;
     if constexpr (kExchange)
-        epoch = peer::header_of(xch.g, xch.g.rank)->fused_seq[blockIdx.x] + 1;
+        epoch = *((volatile unsigned long long*)&peer::header_of(xch.g, xch.g.rank)->fused_epoch) + 1;
     int it = 0;
     for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
         const int c0 = strip * TC;
@@ -280,7 +280,16 @@ reduce_samples_tma_kernel(const double* __restrict__ Lp, long sLi, long sLt,
              strip += kConsumerWarps * 32 * (int)gridDim.x)
             peer::wait_flag(&mine->done[strip], epoch, mine, peer::kWaitDone);
         samples_consumer_barrier();
-        if (threadIdx.x == 0) mine->fused_seq[blockIdx.x] = epoch;
+        if (threadIdx.x == 0) {
+            // the last CTA to leave publishes the epoch for the next launch (all CTAs of this
+            // launch are resident and have read the old value long before)
+            __threadfence();
+            if (atomicAdd(&mine->fused_tickets, 1u) == gridDim.x - 1) {
+                mine->fused_tickets = 0;
+                __threadfence();
+                *((volatile unsigned long long*)&mine->fused_epoch) = epoch;
+            }
+        }
     }
 }
 

@@ -36,6 +36,9 @@ class Region:
         self.coll_finish = [[0] * max_ctas for _ in range(world)]
         self.buf = []                                               # chunk -> ('partial'|'sum', n)
         self.launch = 0                                             # launch this rank's stream is in
+        # all-gather of column blocks
+        self.gathered = [0] * world                                 # block of rank r -> launch
+        self.gather_readers = 0
 
 
 def fused_cta(mem, world, rank, cta, grid, nstrips):
@@ -123,6 +126,42 @@ def allreduce_cta(mem, world, rank, cta, grid, nchunks):
     yield
 
 
+def allgather_cta(mem, world, rank, cta, grid, launch):
+    """One CTA of peer_allgather_columns_kernel (push between a start and a finish barrier)."""
+    mine = mem[rank]
+    epoch = mine.coll_seq[cta] + 1
+    yield
+    for p in range(world):
+        mem[p].coll_start[rank][cta] = epoch
+        yield
+    for p in range(world):
+        while mine.coll_start[p][cta] < epoch:
+            yield
+    if cta == 0:                                                # this CTA's share of the block
+        for p in range(world):
+            assert mem[p].gather_readers == 0, 'block pushed under a reader of the old contents'
+            mem[p].gathered[rank] = launch
+            yield
+    for p in range(world):
+        mem[p].coll_finish[rank][cta] = epoch
+        yield
+    for p in range(world):
+        while mine.coll_finish[p][cta] < epoch:
+            yield
+    mine.coll_seq[cta] = epoch
+    yield
+
+
+def gather_reader_kernel(mem, world, rank, launch):
+    mine = mem[rank]
+    mine.gather_readers += 1
+    for r in range(world):
+        assert mine.gathered[r] == launch, 'gathered matrix incomplete or from another launch'
+        yield
+    mine.gather_readers -= 1
+    yield
+
+
 def producer_kernel(mem, rank, nchunks, launch):
     """The kernel that writes this rank's partial before the all-reduce of `launch`."""
     mine = mem[rank]
@@ -146,6 +185,9 @@ def rank_stream(mem, world, rank, plan, rng):
         if kind == 'fused':
             kernels = [[fused_cta(mem, world, rank, b, grid, size) for b in range(grid)],
                        [reader_kernel(mem, rank, size, launch_of(plan, launch, 'fused'))]]
+        elif kind == 'allgather':
+            kernels = [[allgather_cta(mem, world, rank, b, grid, launch) for b in range(grid)],
+                       [gather_reader_kernel(mem, world, rank, launch)]]
         else:
             kernels = [[producer_kernel(mem, rank, size, launch)],
                        [allreduce_cta(mem, world, rank, b, grid, size) for b in range(grid)],
@@ -217,10 +259,15 @@ def test_allreduce_protocol(world):
 
 
 def test_mixed_sequence_as_in_an_iteration():
-    """A GPNH-like iteration: fused k x d sum, then the small statistics all-reduce, repeated."""
+    """A GPNH-like iteration: fused k x d sum, then the small statistics all-reduce, repeated;
+    and an AA-like one with the all-gather of the column blocks in between."""
     plan = [('fused', 4, 6), ('allreduce', 1, 1)] * 6
     for seed in range(30):
         run(3, plan, seed)
+    plan = [('fused', 4, 6), ('allgather', 2, 0), ('allreduce', 1, 1), ('allgather', 1, 0)] * 4
+    for seed in range(30):
+        run(3, plan, seed)
+        run(4, plan, seed, bias=[40, 1, 40, 40])
 
 
 def test_the_model_catches_a_broken_protocol():

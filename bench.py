@@ -1,22 +1,31 @@
 #!/usr/bin/env python
-"""Headline benchmark: GPNH / AA alternating iterations per second at HadISST shape.
+"""Headline benchmark: AA and GPNH outer (alternating) iterations per second at HadISST shape.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload gpnh|aa] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload both|aa|gpnh] [--no-stress] [--no-strong] [--no-numba]
 
-A "step" is one outer alternating iteration (dictionary update + weights update +
-cost bookkeeping) of the reference's loop (`_iterate_gpnh_convex_coding`,
-gpnh_convex_coding.py:282-402, or `_iterate_aa`, archetypal_analysis.py:534-670) on a
-synthetic anomaly matrix of HadISST shape (1620 training months x 44 000 ocean
-cells, fp64, k = 8), BASELINE.json configs[1] (GPNH, default) / configs[0] (AA).
+A "step" is one outer alternating iteration (dictionary update + weights update + cost
+bookkeeping) of the reference's loops -- `_iterate_aa` (archetypal_analysis.py:534-670, the
+workload that owns the outer-level SPG; the drivers' `dictionary_solver_kwargs =
+dict(max_iterations=1)`, bin/run_hadisst_aa.py:160-166) and `_iterate_gpnh_convex_coding`
+(gpnh_convex_coding.py:282-402) -- on a synthetic anomaly matrix of HadISST shape (1620
+training months x 44 000 ocean cells, fp64, k = 8): BASELINE.json configs[0] / configs[1].
 
-Printed JSON (one line, rank 0):
-  value    whole-job outer iterations / second with X resident in HBM, device timed
-  e2e      the same through the public NumPy-in / NumPy-out call, host buffers, H2D of
-           X and D2H of the factors inside the timed region
-  roofline the dominant kernel (the streaming pass over X) against the measured HBM peak
+One JSON line (rank 0).  The top-level keys describe the AA workload (BASELINE.json's metric
+names it first); the GPNH workload sits beside it under "gpnh" with the same keys:
+  value         whole-job outer iterations / second with X resident in HBM, device timed
+  e2e           the same through the public NumPy-in / NumPy-out call: host buffers, H2D of X
+                and D2H of the factors inside the timed region
+  roofline      the slower streaming pass over X against the measured HBM peak
   cpu_baseline  the CPU oracle port of the reference loop timed on this box's host cores
-With N > 1 the sample axis is sharded (weak scaling: every rank owns a full
-1620-row slab; the job is a fit of N x 1620 samples).
+  parity        CUDA path vs the CPU port after the same number of iterations from the same
+                start (asserted: the run exits non-zero when it fails)
+  time_to_converge   one public fit to the drivers' stopping rule
+With N > 1 the sample axis is sharded.  "value" is WEAK scaling (every rank owns a full
+1620-row slab; the job is one fit of N x 1620 samples); "strong_scaling" adds the fixed-size
+figures: the 1620-row HadISST matrix and the 18 000 x 44 000, k = 64 stress shape
+(BASELINE.json configs[4]) split over the N ranks.  "--impl reference" runs the CPU arm on
+the same total number of samples.
 """
 
 import argparse
@@ -33,10 +42,21 @@ for _p in (ROOT, PKG_DIR):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
+if '--impl' in sys.argv and sys.argv[sys.argv.index('--impl') + 1:][:1] == ['reference']:
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every
+    # host core, so the BLAS thread count is set explicitly before
+    # NumPy loads
+    for _v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np   # noqa: E402
 
 T_ROWS, N_FEATURES, N_COMPONENTS = 1620, 44000, 8
+STRESS_ROWS, STRESS_COMPONENTS, STRESS_BLOCKS = 18000, 64, 8
 LAMBDA_W = 0.0
+PARITY_STEPS = 5
+PARITY_COST_RTOL = 1e-8
+PARITY_FACTOR_ATOL = 2e-5
 
 
 def parse_args():
@@ -44,7 +64,7 @@ def parse_args():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--workload', choices=('gpnh', 'aa'), default='gpnh')
+    ap.add_argument('--workload', choices=('both', 'aa', 'gpnh'), default='both')
     ap.add_argument('--impl', choices=('b200', 'reference'), default='b200')
     ap.add_argument('--rows', type=int, default=T_ROWS)
     ap.add_argument('--features', type=int, default=N_FEATURES)
@@ -52,8 +72,16 @@ def parse_args():
     ap.add_argument('--formulation', choices=('stream', 'gram'), default='stream',
                     help="AA only: 'gram' builds K = X X' once and iterates on K (opt-in "
                          "algorithmic variant; the headline numbers use 'stream')")
-    ap.add_argument('--cpu-steps', type=int, default=4,
-                    help='outer iterations of the CPU baseline sample (0 disables it)')
+    ap.add_argument('--cpu-steps', type=int, default=PARITY_STEPS,
+                    help='outer iterations of the CPU baseline / parity sample (0 disables it)')
+    ap.add_argument('--min-timed-ms', type=float, default=50.0,
+                    help='the K-step block is repeated until the timed region is this long')
+    ap.add_argument('--no-stress', action='store_true',
+                    help='skip the 18 000 x 44 000, k = 64 stress shape (BASELINE configs[4])')
+    ap.add_argument('--no-strong', action='store_true',
+                    help='N > 1: skip the strong-scaling (fixed total size) measurements')
+    ap.add_argument('--no-numba', action='store_true',
+                    help='reference arm: skip timing the real (Numba) reference from baseline/_ref')
     return ap.parse_args()
 
 
@@ -151,43 +179,88 @@ class ClockSampler:
                 'reasons': sorted(self.reasons), 'samples': len(self.sm), 'source': self.source}
 
 
-def make_problem(args, rank=0, world=1):
-    """Host-generated inputs, identical for the CUDA path and the CPU arm
-    (BASELINE.md section 3).  Each rank owns a full slab of `rows` samples."""
+# ---------------------------------------------------------------------------
+# problems (host generated, identical for the CUDA path and the CPU arm)
+# ---------------------------------------------------------------------------
+
+def slab(args, rank):
+    """Rank `rank`'s slab of the weak-scaling problem: a full HadISST-shaped matrix."""
     from convex_dim_red.datasets import synthetic_field
+    return synthetic_field(args.rows, args.features, seed=rank)
+
+
+def initial_factors(workload, T, d, k, rank, world):
+    """(weights of this rank's rows, replicated dictionary) in the single-process draw order."""
     from convex_dim_red.stochastic_matrices import right_stochastic_matrix
-    T, d, k = args.rows, args.features, args.components
-    X = synthetic_field(T, d, seed=rank)
-    rs = np.random.RandomState(1000 + rank)
-    if args.workload == 'gpnh':
-        # the dictionary is replicated: every rank draws the same one
-        W0 = np.sqrt(0.4 / k) * np.random.RandomState(0).randn(d, k)
-        Z0 = right_stochastic_matrix((T, k), rs)
-        return X, Z0, W0
-    # the dictionary (k x total samples) is replicated; the weights are this rank's rows
-    C0 = right_stochastic_matrix((k, T * world), np.random.RandomState(7))
-    Z0 = right_stochastic_matrix((T, k), rs)
-    return X, Z0, C0
+    Z0 = right_stochastic_matrix((T, k), np.random.RandomState(1000 + rank))
+    if workload == 'gpnh':
+        return Z0, np.sqrt(0.4 / k) * np.random.RandomState(0).randn(d, k)
+    return Z0, right_stochastic_matrix((k, T * world), np.random.RandomState(7))
 
 
-def cpu_steps(args, X, Z0, F0, n_steps):
-    """The reference loop (oracle port: NumPy/BLAS contractions + C per-sample QPs,
-    same pass structure as the reference) for n_steps outer iterations."""
+def stacked_problem(args, workload, world):
+    """The whole weak-scaling job on one host: the slabs of all ranks stacked."""
+    X = np.concatenate([slab(args, r) for r in range(world)], axis=0) if world > 1 \
+        else slab(args, 0)
+    parts = [initial_factors(workload, args.rows, args.features, args.components, r, world)
+             for r in range(world)]
+    Z0 = np.concatenate([p[0] for p in parts], axis=0)
+    return X, Z0, parts[0][1]
+
+
+def stress_block(block, d, n_rows):
+    """Rows [block * n_rows, (block + 1) * n_rows) of the stress matrix (block-seeded so that
+    every split over 1 / 2 / 4 / 8 ranks sees the same 18 000 x 44 000 matrix)."""
+    from convex_dim_red.stochastic_matrices import right_stochastic_matrix
+    sources = np.random.RandomState(499).standard_normal((12, d))
+    rs = np.random.RandomState(500 + block)
+    x = right_stochastic_matrix((n_rows, 12), rs).dot(sources)
+    x += 0.5 * rs.standard_normal((n_rows, d))
+    return x
+
+
+def stress_blocks(rank, world):
+    per = STRESS_BLOCKS // world
+    return range(rank * per, (rank + 1) * per), STRESS_ROWS // STRESS_BLOCKS
+
+
+def stress_rows(rank, world, d):
+    """This rank's rows of the stress matrix."""
+    blocks, rows = stress_blocks(rank, world)
+    return np.concatenate([stress_block(b, d, rows) for b in blocks], axis=0)
+
+
+def stress_factors(workload, rank, world, d):
+    from convex_dim_red.stochastic_matrices import right_stochastic_matrix
+    k = STRESS_COMPONENTS
+    blocks, rows = stress_blocks(rank, world)
+    Z0 = np.concatenate([right_stochastic_matrix((rows, k), np.random.RandomState(2000 + b))
+                         for b in blocks], axis=0)
+    if workload == 'gpnh':
+        return Z0, np.sqrt(0.4 / k) * np.random.RandomState(0).randn(d, k)
+    return Z0, right_stochastic_matrix((k, STRESS_ROWS), np.random.RandomState(7))
+
+
+# ---------------------------------------------------------------------------
+# CPU arm (oracle port of the reference loop)
+# ---------------------------------------------------------------------------
+
+def cpu_steps(workload, X, Z0, F0, n_steps):
+    """The reference loop (oracle port: NumPy/BLAS contractions + C per-sample QPs, same pass
+    structure as the reference) for n_steps outer iterations from the given start."""
     from oracle import convex_oracle as orc
-    trace = float(np.sum(X * X))
+    trace = float(np.einsum('ij,ij->', X, X))
     times = []
-    if args.workload == 'gpnh':
+    if workload == 'gpnh':
         out = orc.iterate_gpnh(X, Z0.copy(), F0.copy(), lambda_W=LAMBDA_W, tolerance=0.0,
                                max_iterations=n_steps, trace_XtX=trace,
                                require_monotonic_cost_decrease=False, iter_times_out=times)
-        cost = out[2]
-    else:
-        out = orc.iterate_aa(X, Z0.copy(), F0.copy(), np.ones(F0.shape[0]), tolerance=0.0,
-                             max_iterations=n_steps, trace_XXt=trace,
-                             dictionary_solver_kwargs=dict(max_iterations=1),
-                             require_monotonic_cost_decrease=False, iter_times_out=times)
-        cost = out[3]
-    return times, cost
+        return times, float(out[2]), out[0], out[1]
+    out = orc.iterate_aa(X, Z0.copy(), F0.copy(), np.ones(F0.shape[0]), tolerance=0.0,
+                         max_iterations=n_steps, trace_XXt=trace,
+                         dictionary_solver_kwargs=dict(max_iterations=1),
+                         require_monotonic_cost_decrease=False, iter_times_out=times)
+    return times, float(out[3]), out[0], out[1]
 
 
 def blas_threads():
@@ -199,54 +272,255 @@ def blas_threads():
         return os.cpu_count()
 
 
-def run_reference(args):
-    rank = int(os.environ.get('RANK', '0'))
-    if rank != 0:
-        return
-    X, Z0, F0 = make_problem(args)
-    # run `warmup + steps` outer iterations from the same start as the CUDA arm and
-    # time the last `steps` of them (per-iteration wall times from the loop itself)
-    times, cost = cpu_steps(args, X, Z0, F0, args.warmup + args.steps)
+PORT_NOTE = ('oracle port of the reference loop (NumPy/OpenBLAS passes over X with all host '
+             'threads + C per-sample QPs); the real Numba reference makes 11+ passes per AA '
+             'iteration and is ~30x slower (see numba_reference / profiles)')
+
+
+def metric_name(workload):
+    return '%s_outer_iterations_per_sec_hadisst' % workload
+
+
+def config_dict(args, workload, world):
+    return {'workload': '%s k=%d on synthetic HadISST-shaped anomalies, %d x %d fp64 per GPU '
+                        '(BASELINE.json configs[%d])'
+                        % ('GPNH convex coding' if workload == 'gpnh' else
+                           'archetypal analysis (dictionary SPG max_iterations=1, as '
+                           'bin/run_hadisst_aa.py:160-166)',
+                           args.components, args.rows, args.features,
+                           1 if workload == 'gpnh' else 0),
+            'n_samples_total': args.rows * world, 'n_features': args.features,
+            'n_components': args.components, 'lambda_W': LAMBDA_W,
+            'dictionary_solver_kwargs': None if workload == 'gpnh' else {'max_iterations': 1},
+            'formulation': ('streaming (X read from HBM every pass; 2 passes/iter GPNH, 4 AA)'
+                            if args.formulation == 'stream' or workload == 'gpnh' else
+                            'gram (K = X X^T built once, 2 passes over the L2-resident K per '
+                            'iteration; no HBM roofline applies)'),
+            'l2_policy': 'X (%.0f MB per GPU) is larger than the 126 MB L2; no explicit flush'
+                         % (8e-6 * args.rows * args.features),
+            'sharding': 'sample axis, %d rank(s)' % world}
+
+
+def numba_reference(args, workload):
+    """Time the real reference (installed unmodified under baseline/_ref) in a subprocess."""
+    script = os.path.join(ROOT, 'baseline', 'time_reference.py')
+    if args.no_numba or not os.path.isdir(os.path.join(ROOT, 'baseline', '_ref', 'convex_dim_red')):
+        return {'unavailable': 'baseline/_ref not installed or --no-numba'}
+    try:
+        out = subprocess.run([sys.executable, script, '--workload', workload, '--rows',
+                              str(args.rows), '--features', str(args.features), '--components',
+                              str(args.components), '--iterations', '2'],
+                             capture_output=True, text=True, timeout=900)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as exc:              # the baseline arm must not take the bench line down
+        return {'unavailable': 'baseline/time_reference.py failed: %r' % (exc,)}
+
+
+def reference_line(args, workload, world):
+    X, Z0, F0 = stacked_problem(args, workload, world)
+    # `warmup + steps` outer iterations from the same start as the CUDA arm; the last `steps`
+    # are timed (per-iteration wall times from the loop itself)
+    times, cost, _, _ = cpu_steps(workload, X, Z0, F0, args.warmup + args.steps)
     timed = max(sum(times[args.warmup:]), 1e-9)
     value = args.steps / timed
     cores = blas_threads()
     line = {
-        'impl': 'reference', 'metric': metric_name(args), 'value': value, 'unit': 'iterations/s',
-        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'impl': 'reference', 'metric': metric_name(workload), 'value': value,
+        'unit': 'iterations/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * timed / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': config_dict(args, 1),
+        'config': config_dict(args, workload, world),
         'cpu_baseline': {'value': value, 'unit': 'iterations/s', 'cores': cores, 'kind': 'port',
-                         'sample': '%d outer iterations after %d untimed, oracle port of the '
-                                   'reference loop (NumPy/OpenBLAS passes + C per-sample QPs)'
-                                   % (args.steps, args.warmup)},
+                         'host_cpus': os.cpu_count(),
+                         'sample': '%d outer iterations after %d untimed on all %d x %d samples; %s'
+                                   % (args.steps, args.warmup, X.shape[0], X.shape[1], PORT_NOTE)},
         'e2e': {'value': value, 'unit': 'iterations/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
         'final_cost': cost,
     }
-    print(json.dumps(line))
+    return line
 
 
-def metric_name(args):
-    return ('gpnh_outer_iterations_per_sec_hadisst' if args.workload == 'gpnh'
-            else 'aa_outer_iterations_per_sec_hadisst')
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    world = args.gpus
+    workloads = ('aa', 'gpnh') if args.workload == 'both' else (args.workload,)
+    lines = {w: reference_line(args, w, world) for w in workloads}
+    if world == 1:
+        for w in workloads:
+            lines[w]['numba_reference'] = numba_reference(args, w)
+    head = lines[workloads[0]]
+    if len(workloads) > 1:
+        head['gpnh'] = lines['gpnh']
+    print(json.dumps(head))
 
 
-def config_dict(args, world):
-    return {'workload': '%s k=%d on synthetic HadISST-shaped anomalies, %d x %d fp64 per GPU '
-                        '(BASELINE.json configs[%d])'
-                        % ('GPNH convex coding' if args.workload == 'gpnh' else
-                           'archetypal analysis (dictionary SPG max_iterations=1)',
-                           args.components, args.rows, args.features,
-                           1 if args.workload == 'gpnh' else 0),
-            'n_samples_total': args.rows * world, 'n_features': args.features,
-            'n_components': args.components, 'lambda_W': LAMBDA_W,
-            'formulation': ('streaming (X read from HBM every pass; 2 passes/iter GPNH, 4 AA)'
-                            if args.formulation == 'stream' else
-                            'gram (K = X X^T built once, 2 passes over the L2-resident K per '
-                            'iteration; no HBM roofline applies)'),
-            'l2_policy': 'X (570 MB per GPU) is larger than the 126 MB L2; no explicit flush',
-            'sharding': 'sample axis, %d rank(s)' % world}
+# ---------------------------------------------------------------------------
+# CUDA arm
+# ---------------------------------------------------------------------------
+
+def parity_block(args, workload, X, Z0, F0, cpu_result):
+    """CUDA path vs the CPU port after the same number of outer iterations from the same
+    start, through the public `_iterate_*` call."""
+    import bench_harness as bh
+    times, cpu_cost, cpu_Z, cpu_F = cpu_result
+    n = len(times)
+    Zg, Fg, gpu_cost = bh.gpu_fit(workload, X, Z0, F0, n)
+    dz = float(np.max(np.abs(Zg - cpu_Z)))
+    df = float(np.max(np.abs(Fg - cpu_F)))
+    rel = abs(gpu_cost - cpu_cost) / abs(cpu_cost)
+    ok = bool(rel <= PARITY_COST_RTOL and dz <= PARITY_FACTOR_ATOL and df <= PARITY_FACTOR_ATOL)
+    return {'ok': ok, 'iterations': n, 'gpu_cost': gpu_cost, 'cpu_cost': cpu_cost,
+            'cost_rel_diff': rel, 'cost_rtol': PARITY_COST_RTOL,
+            'weights_max_abs_diff': dz, 'dictionary_max_abs_diff': df,
+            'factor_atol': PARITY_FACTOR_ATOL,
+            'against': 'CPU oracle port, same host-generated inputs and start'}
+
+
+def sharded_parity_block(args, workload, Xl, Z0l, F0, rank, world, comm):
+    """N > 1: the sharded fit against a one-GPU fit of the stacked rows on rank 0."""
+    import bench_harness as bh
+    _, _, cost_sharded = bh.gpu_fit(workload, Xl, Z0l, F0, PARITY_STEPS, comm=comm)
+    block = None
+    if rank == 0:
+        X, Z0, F0s = stacked_problem(args, workload, world)
+        _, _, cost_one = bh.gpu_fit(workload, X, Z0, F0s, PARITY_STEPS)
+        rel = abs(cost_sharded - cost_one) / abs(cost_one)
+        block = {'ok': bool(rel <= PARITY_COST_RTOL), 'iterations': PARITY_STEPS,
+                 'sharded_cost': cost_sharded, 'one_gpu_cost': cost_one, 'cost_rel_diff': rel,
+                 'cost_rtol': PARITY_COST_RTOL,
+                 'against': 'one-GPU fit of the %d stacked rows on rank 0' % X.shape[0]}
+    bh.barrier(world)
+    return block
+
+
+def workload_block(args, workload, X, Xd, rank, world, comm, sampler, hbm_peak, peak_src):
+    import bench_harness as bh
+    T, d, k = args.rows, args.features, args.components
+    Z0, F0 = initial_factors(workload, T, d, k, rank, world)
+    res = bh.run_workload(args, workload, X, Z0, F0, Xd, rank, world, comm)
+    eng, step = res.pop('engine'), res.pop('step')
+    ms = res['ms_per_step']
+    gram_mode = workload == 'aa' and args.formulation == 'gram'
+    block = {
+        'metric': metric_name(workload), 'value': world * 1e3 / ms, 'unit': 'iterations/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+        'timed_steps': res['timed_steps'], 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': config_dict(args, workload, world),
+        'gpu_launches': res['launches_per_step'] * res['timed_steps'],
+        'launches_per_step': res['launches_per_step'], 'final_cost': res['final_cost'],
+    }
+    pass_bytes = 8.0 * T * d
+    if not gram_mode:
+        t_s, t_f, t_qp, passes = bh.time_passes(args, workload, eng, T, d, k)
+        slow, name = max((t_s, 'reduce_samples_tma_kernel'), (t_f, 'reduce_features_strip_kernel'))
+        roof = {'kernel': name, 'bound': 'hbm', 'achieved': pass_bytes / (slow * 1e-3) / 1e9,
+                'peak': hbm_peak, 'unit': 'GB/s', 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': pass_bytes, 'ms_per_launch': slow, 'traffic': None}
+        roof['frac'] = roof['achieved'] / hbm_peak
+        tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                tr = json.load(fh)
+            roof['traffic'] = tr['dram_bytes_per_launch'].get(name)
+            roof['traffic_source'] = tr['source']
+        block['roofline'] = roof
+        block['kernels'] = {
+            'reduce_samples_ms': t_s, 'reduce_features_ms': t_f,
+            'reduce_samples_gbs': pass_bytes / (t_s * 1e-3) / 1e9,
+            'reduce_features_gbs': pass_bytes / (t_f * 1e-3) / 1e9,
+            'qp_batched_ms': t_qp, 'passes_per_step': passes, 'step_ms': ms,
+            'streaming_share_of_step': passes / 2.0 * (t_s + t_f) / ms,
+            'whole_step_gbs': passes * pass_bytes / (ms * 1e-3) / 1e9,
+            'whole_step_frac_of_hbm_peak': passes * pass_bytes / (ms * 1e-3) / 1e9 / hbm_peak}
+    else:
+        from convex_dim_red import _backend as be
+        t_gram = bh.time_launches(lambda: be.gram(Xd, T, d), reps=3)
+        block['roofline'] = None
+        block['kernels'] = {'gram_build_ms': t_gram,
+                            'gram_build_tflops': 2.0 * T * T * d / (t_gram * 1e-3) / 1e12,
+                            'step_ms': ms}
+    # keep the GPU busy a little longer so that several clock samples land under load (a fixed
+    # count: every rank must issue the same collectives)
+    for _ in range(300):
+        step()
+    bh.barrier(world)
+    del eng, step
+    block['e2e'] = bh.run_e2e(workload, X, Z0, F0, args.steps, world, comm)
+    if world == 1:
+        block['time_to_converge'] = bh.run_to_convergence(workload, X, Z0, F0,
+                                                          formulation=args.formulation)
+        if args.cpu_steps > 0 and rank == 0:
+            cpu = cpu_steps(workload, X, Z0, F0, args.cpu_steps)
+            times = cpu[0]
+            block['cpu_baseline'] = {
+                'value': len(times) / sum(times), 'unit': 'iterations/s', 'cores': blas_threads(),
+                'host_cpus': os.cpu_count(), 'kind': 'port',
+                'sample': 'first %d outer iterations of the same workload from the same start; %s'
+                          % (len(times), PORT_NOTE),
+                'final_cost': cpu[1]}
+            block['parity'] = parity_block(args, workload, X, Z0, F0, cpu)
+            block['time_to_converge']['cpu_estimate_seconds'] = \
+                block['time_to_converge']['iterations'] * sum(times) / len(times)
+    else:
+        block['parity'] = sharded_parity_block(args, workload, X, Z0, F0, rank, world, comm)
+    return block
+
+
+def fixed_size_block(args, name, workload, X, Xd, Z0, F0, rank, world, comm, flops_per_step):
+    """A fixed-total-size (strong scaling) measurement: this rank's rows of the problem."""
+    import bench_harness as bh
+    res = bh.run_workload(args, workload, X, Z0, F0, Xd, rank, world, comm)
+    res.pop('engine')
+    res.pop('step')
+    ms = res['ms_per_step']
+    out = {'workload': name, 'value': 1e3 / ms, 'unit': 'iterations/s', 'ms_per_step': ms,
+           'timed_steps': res['timed_steps'], 'rows_per_gpu': int(X.shape[0]), 'n_gpus': world,
+           'launches_per_step': res['launches_per_step'], 'final_cost': res['final_cost'],
+           'tflops': flops_per_step / (ms * 1e-3) / 1e12,
+           'gbs_streaming': flops_per_step / (2.0 * Z0.shape[1]) * 8.0 / (ms * 1e-3) / 1e9}
+    return out
+
+
+def strong_scaling(args, rank, world, comm):
+    """Fixed-size problems split over the ranks: the HadISST matrix (1620 rows, k = 8) and --
+    unless --no-stress -- the 18 000 x 44 000, k = 64 stress shape (BASELINE configs[4])."""
+    from convex_dim_red import _backend as be
+    from convex_dim_red._dist import shard_bounds
+    from convex_dim_red.datasets import synthetic_field
+    out = {}
+    d, k = args.features, args.components
+    if world > 1 and not args.no_strong:
+        X = synthetic_field(args.rows, d, seed=0)
+        lo, hi = shard_bounds(args.rows, world, rank)
+        Xl = np.ascontiguousarray(X[lo:hi])
+        del X
+        Xd = be.to_device_padded(Xl)
+        for wl in ('aa', 'gpnh'):
+            Zfull, F0 = initial_factors(wl, args.rows, d, k, 0, 1)
+            passes = 4 if wl == 'aa' else 2
+            out['hadisst_' + wl] = fixed_size_block(
+                args, '%s k=%d, %d x %d split over %d GPUs' % (wl, k, args.rows, d, world), wl,
+                Xl, Xd, np.ascontiguousarray(Zfull[lo:hi]), F0, rank, world, comm,
+                passes * 2.0 * k * args.rows * d)
+        del Xd
+        be.torch_mod().cuda.empty_cache()
+    if not args.no_stress and STRESS_BLOCKS % world == 0:
+        Xs = stress_rows(rank, world, d)
+        Xd = be.to_device_padded(Xs)
+        for wl in ('gpnh', 'aa'):
+            Z0, F0 = stress_factors(wl, rank, world, d)
+            passes = 4 if wl == 'aa' else 2
+            out['stress_' + wl] = fixed_size_block(
+                args, '%s k=%d, %d x %d split over %d GPU(s) (BASELINE.json configs[4])'
+                % (wl, STRESS_COMPONENTS, STRESS_ROWS, d, world), wl, Xs, Xd, Z0, F0, rank,
+                world, comm, passes * 2.0 * STRESS_COMPONENTS * STRESS_ROWS * d)
+        del Xd, Xs
+        be.torch_mod().cuda.empty_cache()
+    return out
 
 
 def run_b200(args):
@@ -262,48 +536,41 @@ def run_b200(args):
         os.environ.setdefault('NCCL_PROTO', 'LL')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     from convex_dim_red import _backend as be
-    from convex_dim_red import _bench_support as bs
+    from convex_dim_red._dist import Comm
+    comm = Comm() if world > 1 else None
+    hbm_peak, peak_src = peaks()
+    workloads = ('aa', 'gpnh') if args.workload == 'both' else (args.workload,)
 
-    X, Z0, F0 = make_problem(args, rank, world)
-    result = bs.run_benchmark(args, X, Z0, F0, rank, world, ClockSampler(local_rank))
+    X = slab(args, rank)
+    Xd = be.to_device_padded(X)
+    sampler = ClockSampler(local_rank)
+    sampler.__enter__()
+    blocks = {}
+    for wl in workloads:
+        blocks[wl] = workload_block(args, wl, X, Xd, rank, world, comm, sampler, hbm_peak, peak_src)
+    sampler.__exit__(None, None, None)
+    del Xd
+    torch.cuda.empty_cache()
+    strong = strong_scaling(args, rank, world, comm)
+
     if rank == 0:
-        peak, peak_src = peaks()
-        roof = result['roofline']
-        if roof is not None:
-            roof.update({'bound': 'hbm', 'peak': peak, 'unit': 'GB/s',
-                         'frac': roof['achieved'] / peak, 'peak_source': peak_src})
-            tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
-            if os.path.exists(tpath):
-                with open(tpath) as fh:
-                    tr = json.load(fh)
-                roof['traffic'] = tr['dram_bytes_per_launch'].get(roof['kernel'])
-                roof['traffic_source'] = tr['source']
-        line = {
-            'metric': metric_name(args), 'value': result['value'], 'unit': 'iterations/s',
-            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': result['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': config_dict(args, world), 'clocks': result['clocks'],
-            'e2e': result['e2e'], 'gpu_launches': result['gpu_launches'],
-            'roofline': roof, 'kernels': result['kernels'], 'final_cost': result['final_cost'],
-            'time_to_converge': result['time_to_converge'],
-        }
-        if args.cpu_steps > 0 and world == 1:
-            times, cost = cpu_steps(args, X, Z0, F0, args.cpu_steps)
-            line['cpu_baseline'] = {
-                'value': args.cpu_steps / sum(times), 'unit': 'iterations/s',
-                'cores': blas_threads(), 'kind': 'port',
-                'sample': 'first %d outer iterations of the same workload from the same start '
-                          '(oracle port of the reference loop)' % args.cpu_steps,
-                'final_cost': cost}
-            ttc = line.get('time_to_converge')
-            if ttc:
-                # not run: iterations of the converged CUDA fit x the CPU time per iteration
-                ttc['cpu_estimate_seconds'] = ttc['iterations'] * sum(times) / args.cpu_steps
-        print(json.dumps(line))
+        head = blocks[workloads[0]]
+        head['clocks'] = sampler.summary()
+        if len(workloads) > 1:
+            head['gpnh'] = blocks['gpnh']
+            head['gpu_launches'] += blocks['gpnh']['gpu_launches']
+        if strong:
+            head['strong_scaling'] = strong
+        print(json.dumps(head))
+        sys.stdout.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:
+        bad = [w for w in workloads if blocks[w].get('parity') and not blocks[w]['parity']['ok']]
+        if bad:
+            sys.stderr.write('bench.py: PARITY FAILED for %s\n' % ', '.join(bad))
+            sys.exit(3)
 
 
 def main():

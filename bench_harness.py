@@ -1,0 +1,216 @@
+"""Timing harness behind ``bench.py`` (test / measurement infrastructure, not product code).
+
+It drives the engines of the product package the way ``fit_transform`` does -- one
+``initial_cost()`` and then repeated ``iteration()`` calls, replayed from a CUDA graph -- and
+times them with CUDA events on the launching stream."""
+
+import time
+
+import numpy as np
+
+from convex_dim_red import _backend as be
+
+DICT_KW = dict(max_iterations=1)       # bin/run_hadisst_aa.py:160-166
+
+
+def make_engine(workload, X, Z0, F0, Xd=None, comm=None, formulation='stream', max_iterations=10 ** 6):
+    from convex_dim_red.archetypal_analysis import _AaEngine
+    from convex_dim_red.gpnh_convex_coding import _GpnhEngine
+    if workload == 'gpnh':
+        return _GpnhEngine(X, Z0, F0, lambda_W=0.0, tolerance=0.0, max_iterations=max_iterations,
+                           require_monotonic_cost_decrease=False, X_device=Xd, comm=comm)
+    k = F0.shape[0]
+    if formulation == 'gram':
+        from convex_dim_red.archetypal_analysis import _ShapeOnly
+        T, d = X.shape
+        trace = float(be.frobenius_sq(Xd, T, d).item())
+        return _AaEngine(_ShapeOnly((T, T)), Z0, F0, np.ones(k), 'kernel', tolerance=0.0,
+                         max_iterations=max_iterations, require_monotonic_cost_decrease=False,
+                         dictionary_solver_kwargs=DICT_KW, data_device=be.gram(Xd, T, d),
+                         trace_data=trace, grad_scale=1.0 / T)
+    return _AaEngine(X, Z0, F0, np.ones(k), 'feature', tolerance=0.0,
+                     max_iterations=max_iterations, require_monotonic_cost_decrease=False,
+                     dictionary_solver_kwargs=DICT_KW, data_device=Xd, comm=comm)
+
+
+def time_launches(fn, reps=10):
+    """Average duration (ms) of ``fn`` over ``reps`` back-to-back calls, CUDA events on the
+    current stream, after one untimed call."""
+    torch = be.torch_mod()
+    fn()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def max_over_ranks(value, world):
+    if world == 1:
+        return value
+    torch = be.torch_mod()
+    import torch.distributed as dist
+    t = torch.tensor([value], dtype=torch.float64, device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    be.torch_mod().cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        be.torch_mod().cuda.synchronize()
+
+
+def time_steps(step, steps, warmup, world, min_timed_ms):
+    """`warmup` untimed steps, then blocks of exactly `steps` steps until the timed region
+    lasts at least `min_timed_ms` (one block always runs).  Barrier + synchronize on both
+    sides, CUDA events, max over ranks.  Returns (ms per step, timed steps)."""
+    torch = be.torch_mod()
+    for _ in range(warmup):
+        step()
+    barrier(world)
+    # one probing block decides how many blocks the timed region needs (same on all ranks)
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    probe_ms = max_over_ranks(e0.elapsed_time(e1), world)
+    blocks = max(1, int(np.ceil(min_timed_ms / max(probe_ms, 1e-3))))
+    barrier(world)
+    e0.record()
+    for _ in range(blocks * steps):
+        step()
+    e1.record()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    return ms / (blocks * steps), blocks * steps
+
+
+def run_workload(args, workload, X, Z0, F0, Xd, rank, world, comm, pass_shapes=True):
+    """Device-timed steps of one workload with X resident, the streaming passes on their own,
+    and the launch count of a steady-state step."""
+    torch = be.require_cuda()
+    lib = be.library()
+    T, d = X.shape
+    k = Z0.shape[1]
+    eng = make_engine(workload, X, Z0, F0, Xd, comm, getattr(args, 'formulation', 'stream'))
+    eng.initial_cost()
+    eng.iteration()                                  # eager: first warm-up step
+    n1 = lib.cdr_launch_count()
+    eng.iteration()                                  # a steady-state step, counted
+    launches_per_step = lib.cdr_launch_count() - n1
+    use_graph = not (be.graphs_disabled() or (world > 1 and not be.graph_collectives()))
+    graph = be.capture_graph(eng.iteration) if use_graph else None
+    step = graph.replay if graph is not None else eng.iteration
+    ms, timed = time_steps(step, args.steps, max(args.warmup - 2, 0), world, args.min_timed_ms)
+    st = eng.state.read()
+    out = {'ms_per_step': ms, 'timed_steps': timed, 'launches_per_step': int(launches_per_step),
+           'final_cost': st.cost, 'iterations_run': st.n_iter, 'engine': eng, 'step': step}
+    return out
+
+
+def time_passes(args, workload, eng, T, d, k):
+    """The two streaming passes and the batched QP of a step, each timed alone."""
+    ws = eng.ws
+    if workload == 'gpnh':
+        t_samples = time_launches(lambda: be.reduce_samples(
+            eng.Z, 1, k, eng.X, T, d, k, eng.WT, ws, E=eng.P if k <= 16 else None))
+        t_features = time_launches(lambda: be.reduce_features(eng.WT, eng.X, T, d, k, eng.XWt, ws))
+        zsave = eng.Z.clone()
+        t_qp = time_launches(lambda: (eng.Z.copy_(zsave), be.quad_simplex_spg_batched(
+            eng.WtW, None, eng.XWt, 1, eng.ldt, eng.Z, T, k, eng.params)), reps=5)
+        passes = 2
+    else:
+        t_samples = time_launches(lambda: be.reduce_samples(
+            eng.D, eng.ldt, 1, eng.X, T, d, k, eng.tmp_kd, ws))
+        t_features = time_launches(lambda: be.reduce_features(eng.tmp_kd, eng.X, T, d, k, eng.DK, ws))
+        zsave = eng.Z.clone()
+        t_qp = time_launches(lambda: (eng.Z.copy_(zsave), be.quad_simplex_spg_batched(
+            eng.CKCt, eng.alpha, eng.CK, 1, eng.ldt, eng.Z, T, k, eng.w_params)), reps=5)
+        passes = 4
+    return t_samples, t_features, t_qp, passes
+
+
+def run_e2e(workload, X, Z0, F0, steps, world, comm=None):
+    """One public-API call of `steps` outer iterations: X (pinned host memory) is uploaded
+    inside the timed region, the factors and the cost history come back as NumPy arrays."""
+    torch = be.torch_mod()
+    from convex_dim_red import archetypal_analysis as aa
+    from convex_dim_red import gpnh_convex_coding as gp
+    Xp = torch.from_numpy(X).pin_memory()
+    Xn = Xp.numpy()
+    K = steps
+
+    def call():
+        if workload == 'gpnh':
+            out = gp._iterate_gpnh_convex_coding(
+                Xn, Z0, F0, lambda_W=0.0, tolerance=0.0, max_iterations=K,
+                require_monotonic_cost_decrease=False, comm=comm)
+        else:
+            out = aa._iterate_aa(
+                Xn, Z0, F0, np.ones(F0.shape[0]), tolerance=0.0, max_iterations=K,
+                require_monotonic_cost_decrease=False, dictionary_solver_kwargs=DICT_KW,
+                comm=comm)
+        return out[0].nbytes + out[1].nbytes + 8 * K
+
+    call()                                   # untimed warm-up call (allocator, module load)
+    barrier(world)
+    t0 = time.perf_counter()
+    d2h = call()
+    torch.cuda.synchronize()
+    elapsed = max_over_ranks(time.perf_counter() - t0, world)
+    h2d = X.nbytes + Z0.nbytes + F0.nbytes
+    return {'value': world * K / elapsed, 'unit': 'iterations/s',
+            'h2d_bytes_per_step': h2d / K, 'd2h_bytes_per_step': d2h / K,
+            'call': 'one _iterate_%s call of %d outer iterations (the body of fit_transform): '
+                    'X uploaded once from pinned host memory, factors read back'
+                    % ('gpnh_convex_coding' if workload == 'gpnh' else 'aa', K),
+            'seconds': elapsed}
+
+
+def run_to_convergence(workload, X, Z0, F0, comm=None, tolerance=1e-4, max_iterations=10000,
+                       formulation='stream'):
+    """Wall time of one public-API fit to the drivers' stopping rule (abs_delta_f, tolerance
+    1e-4 as in bin/run_hadisst_aa_wrapper.sh:44, max_iterations 10 000), host buffers in,
+    factors out."""
+    torch = be.torch_mod()
+    from convex_dim_red import archetypal_analysis as aa
+    from convex_dim_red import gpnh_convex_coding as gp
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    if workload == 'gpnh':
+        out = gp._iterate_gpnh_convex_coding(X, Z0, F0, lambda_W=0.0, tolerance=tolerance,
+                                             max_iterations=max_iterations, comm=comm)
+        cost, n_iter = out[2], out[3]
+    else:
+        out = aa._iterate_aa(X, Z0, F0, np.ones(F0.shape[0]), tolerance=tolerance,
+                             max_iterations=max_iterations, dictionary_solver_kwargs=DICT_KW,
+                             comm=comm, formulation=formulation)
+        cost, n_iter = out[3], out[4]
+    torch.cuda.synchronize()
+    return {'seconds': time.perf_counter() - t0, 'iterations': int(n_iter) + 1,
+            'tolerance': tolerance, 'stopping_criterion': 'abs_delta_f', 'cost': float(cost)}
+
+
+def gpu_fit(workload, X, Z0, F0, n_iter, comm=None):
+    """`n_iter` outer iterations through the public API; returns (weights, factor, cost)."""
+    from convex_dim_red import archetypal_analysis as aa
+    from convex_dim_red import gpnh_convex_coding as gp
+    if workload == 'gpnh':
+        out = gp._iterate_gpnh_convex_coding(X, Z0, F0, lambda_W=0.0, tolerance=0.0,
+                                             max_iterations=n_iter, comm=comm,
+                                             require_monotonic_cost_decrease=False)
+        return out[0], out[1], float(out[2])
+    out = aa._iterate_aa(X, Z0, F0, np.ones(F0.shape[0]), tolerance=0.0, max_iterations=n_iter,
+                         dictionary_solver_kwargs=DICT_KW, comm=comm,
+                         require_monotonic_cost_decrease=False)
+    return out[0], out[1], float(out[3])

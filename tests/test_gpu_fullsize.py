@@ -1,7 +1,16 @@
-"""Full-size (BASELINE.json shape) checks through size-independent properties: the oracle
-cannot run at 1620 x 44 000 in seconds, so these verify invariants the domain offers --
-monotone cost, feasibility of the factors, agreement of the trace-form cost with the direct
-residual, linearity of the streaming passes and a checksum of checksums."""
+"""Full-size (BASELINE.json shape) checks.
+
+Two kinds: (i) the CUDA path against the CPU oracle on the same seeded inputs at the
+BASELINE.json shapes themselves -- 1620 x 44 000 k = 8 (configs[0] AA, configs[1] GPNH),
+700 x 41 800 k = 8 (configs[2]: FurthestSum picks and k-means labels, bit-exact) and the
+production width d = 44 000 with k = 64 (configs[4] components, T = 2000 rows) -- the oracle
+needs a few seconds for a handful of outer iterations at these sizes; (ii) size-independent
+properties -- monotone cost, feasibility of the factors, agreement of the trace-form cost
+with the direct residual, linearity of the streaming passes and a checksum of checksums.
+
+Tolerances: iteration counts exact, cost rtol 1e-8, factors atol 2e-5
+(the per-sample SPG stops on a 1e-6 projected-gradient norm, spg.py:392), picks / labels
+bit-exact."""
 
 import numpy as np
 import pytest
@@ -17,6 +26,8 @@ from convex_dim_red import archetypal_analysis as aa                        # no
 from convex_dim_red import gpnh_convex_coding as gp                         # noqa: E402
 from convex_dim_red.datasets import synthetic_field                         # noqa: E402
 from convex_dim_red.stochastic_matrices import right_stochastic_matrix      # noqa: E402
+
+from oracle import convex_oracle as orc                                     # noqa: E402
 
 T, D, K = 1620, 44000, 8
 
@@ -117,3 +128,139 @@ def test_weights_update_idempotent_at_full_batch(hadisst):
     np.testing.assert_allclose(Z2, Z1, rtol=0, atol=5e-6)
     obj = lambda Zm: 0.5 * np.einsum('ti,ij,tj->t', Zm, A, Zm) - np.einsum('ti,it->t', Zm, B)
     assert np.all(obj(Z1) <= obj(Z0) + 1e-12)
+
+
+# ---------------------------------------------------------------------------
+# CUDA path vs the CPU oracle at the BASELINE.json shapes
+# ---------------------------------------------------------------------------
+
+def _close(a, b, rtol, atol=0.0):
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize('lam', [0.0, 0.05])
+def test_gpnh_full_size_vs_oracle(hadisst, lam):
+    """_iterate_gpnh_convex_coding (gpnh_convex_coding.py:282-402), BASELINE configs[1]."""
+    X = hadisst
+    rs = np.random.RandomState(10)
+    W0, Z0 = orc.init_gpnh(X, K, 'random', rs)
+    trace = float(np.sum(X * X))
+    ref = orc.iterate_gpnh(X, Z0.copy(), W0.copy(), lambda_W=lam, tolerance=1e-12,
+                           max_iterations=5, trace_XtX=trace)
+    got = gp._iterate_gpnh_convex_coding(X, Z0.copy(), W0.copy(), lambda_W=lam,
+                                         tolerance=1e-12, max_iterations=5)
+    assert got[3] == ref[3] == 4
+    _close(got[2], ref[2], rtol=1e-8)
+    _close(got[5], ref[5], rtol=1e-5, atol=1e-9)
+    _close(got[0], ref[0], rtol=0, atol=2e-5)
+    _close(got[1], ref[1], rtol=0, atol=2e-5)
+
+
+def test_aa_full_size_vs_oracle(hadisst):
+    """_iterate_aa (archetypal_analysis.py:534-670), BASELINE configs[0], the drivers'
+    dictionary_solver_kwargs=dict(max_iterations=1) (bin/run_hadisst_aa.py:160-166)."""
+    X = hadisst
+    rs = np.random.RandomState(11)
+    C0 = right_stochastic_matrix((K, T), random_state=rs)
+    Z0 = right_stochastic_matrix((T, K), random_state=rs)
+    trace = float(np.sum(X * X))
+    kw = dict(tolerance=1e-12, max_iterations=5, dictionary_solver_kwargs=dict(max_iterations=1))
+    ref = orc.iterate_aa(X, Z0.copy(), C0.copy(), np.ones(K), trace_XXt=trace, **kw)
+    got = aa._iterate_aa(X, Z0.copy(), C0.copy(), np.ones(K), **kw)
+    assert got[4] == ref[4] == 4
+    _close(got[3], ref[3], rtol=1e-8)
+    _close(got[6], ref[6], rtol=1e-5, atol=1e-9)
+    _close(got[0], ref[0], rtol=0, atol=2e-5)
+    _close(got[1], ref[1], rtol=0, atol=2e-5)
+
+
+def test_aa_full_size_inner_spg_iterations_vs_oracle(hadisst):
+    """Two inner SPG iterations per dictionary update exercise the Barzilai-Borwein step and
+    the residual test of spg.py:231-281 at full size."""
+    X = hadisst
+    rs = np.random.RandomState(12)
+    C0 = right_stochastic_matrix((K, T), random_state=rs)
+    Z0 = right_stochastic_matrix((T, K), random_state=rs)
+    trace = float(np.sum(X * X))
+    kw = dict(tolerance=1e-12, max_iterations=2, dictionary_solver_kwargs=dict(max_iterations=2))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ref = orc.iterate_aa(X, Z0.copy(), C0.copy(), np.ones(K), trace_XXt=trace, **kw)
+        got = aa._iterate_aa(X, Z0.copy(), C0.copy(), np.ones(K), **kw)
+    assert got[4] == ref[4]
+    _close(got[3], ref[3], rtol=1e-8)
+    _close(got[1], ref[1], rtol=0, atol=2e-5)
+    _close(got[0], ref[0], rtol=0, atol=2e-5)
+
+
+def test_config3_furthest_sum_and_kmeans_bit_exact():
+    """BASELINE configs[2]: k-means k = 8 with FurthestSum initialisation on a 700 x 41 800
+    field.  Picks vs the oracle's restatement of furthest_sum.py:23-127, labels vs
+    scikit-learn's KMeans itself (the third-party code the drivers call,
+    bin/run_hadisst_kmeans.py:128-131) and vs the oracle: all bit-exact."""
+    from sklearn.cluster import KMeans as SkKMeans
+    from convex_dim_red.furthest_sum import furthest_sum
+    from convex_dim_red.kmeans import kmeans_lloyd
+    Tk, Dk = 700, 41800
+    X = synthetic_field(Tk, Dk, seed=5)
+    start = int(np.random.RandomState(0).randint(Tk))
+    Kmat = X.dot(X.T)
+    Dmat = orc.dissimilarity_from_kernel(Kmat)
+    ref_picks = np.asarray(orc.furthest_sum(Dmat, K, start, [], 10))
+    # device Gram -> dissimilarity -> selection, through the estimator's initialiser
+    C = aa._initialize_kernel_aa_dictionary_furthest_sum(
+        aa._LazyKernel(X), K, start_index=start, n_extra_steps=10)
+    picks = np.argmax(C, axis=1)
+    assert np.array_equal(picks, ref_picks)
+    assert np.array_equal(np.asarray(furthest_sum(Dmat, K, start, [], 10)), ref_picks)
+    labels, centres, inertia, n_iter = kmeans_lloyd(X, X[picks], tol=1e-4, max_iter=300)
+    sk = SkKMeans(n_clusters=K, init=X[ref_picks], n_init=1, algorithm='lloyd', tol=1e-4,
+                  max_iter=300).fit(X)
+    assert labels.dtype == np.int32
+    assert np.array_equal(labels, sk.labels_)
+    assert n_iter == sk.n_iter_
+    _close(inertia, sk.inertia_, rtol=1e-10)
+    _close(centres, sk.cluster_centers_, rtol=0, atol=1e-9)
+    olabels, ocentres, oinertia, on_iter = orc.kmeans_lloyd(X, X[ref_picks], tol=1e-4,
+                                                            max_iter=300)
+    assert np.array_equal(labels, olabels) and n_iter == on_iter
+
+
+@pytest.fixture(scope='module')
+def wide_k64():
+    return synthetic_field(2000, D, seed=6)
+
+
+def test_gpnh_k64_production_width_vs_oracle(wide_k64):
+    """k = 64 at d = 44 000 (BASELINE configs[4] components and width, T = 2000 rows): the
+    kernels chosen for k > 16 at production width."""
+    X = wide_k64
+    k = 64
+    rs = np.random.RandomState(13)
+    W0, Z0 = orc.init_gpnh(X, k, 'random', rs)
+    trace = float(np.sum(X * X))
+    ref = orc.iterate_gpnh(X, Z0.copy(), W0.copy(), lambda_W=0.0, tolerance=1e-12,
+                           max_iterations=3, trace_XtX=trace)
+    got = gp._iterate_gpnh_convex_coding(X, Z0.copy(), W0.copy(), lambda_W=0.0,
+                                         tolerance=1e-12, max_iterations=3)
+    assert got[3] == ref[3]
+    _close(got[2], ref[2], rtol=1e-8)
+    _close(got[0], ref[0], rtol=0, atol=2e-5)
+    _close(got[1], ref[1], rtol=0, atol=2e-5)
+
+
+def test_aa_k64_production_width_vs_oracle(wide_k64):
+    X = wide_k64
+    k, Tn = 64, wide_k64.shape[0]
+    rs = np.random.RandomState(14)
+    C0 = right_stochastic_matrix((k, Tn), random_state=rs)
+    Z0 = right_stochastic_matrix((Tn, k), random_state=rs)
+    trace = float(np.sum(X * X))
+    kw = dict(tolerance=1e-12, max_iterations=3, dictionary_solver_kwargs=dict(max_iterations=1))
+    ref = orc.iterate_aa(X, Z0.copy(), C0.copy(), np.ones(k), trace_XXt=trace, **kw)
+    got = aa._iterate_aa(X, Z0.copy(), C0.copy(), np.ones(k), **kw)
+    assert got[4] == ref[4]
+    _close(got[3], ref[3], rtol=1e-8)
+    _close(got[0], ref[0], rtol=0, atol=2e-5)
+    _close(got[1], ref[1], rtol=0, atol=2e-5)

@@ -74,7 +74,7 @@ typedef struct cdr_loop_state {
     int spg_feval;
     int spg_active;       /* inner SPG still iterating */
     int spg_alpha_set;    /* 0 until the first step length is initialised (spg.py:178-189) */
-    int spg_warnings;     /* bit 0 step below lambda_min, bit 1 feval limit */
+    int spg_warnings;     /* sticky: bit 0 step below lambda_min, bit 1 feval limit, bit 2 iteration limit */
     double tolerance;
     double trace_data;    /* trace(K) or ||X||_F^2 */
     double cost;          /* current cost */
@@ -92,6 +92,7 @@ typedef struct cdr_loop_state {
     double resinf;
     double penalty;       /* GPNH: lambda_W * phi(W) */
     double f_mem[CDR_MAX_MEMORY];
+    unsigned int tickets[4]; /* "last CTA" counters of the fused kernels; zero between launches */
 } cdr_loop_state;
 
 typedef cdr_loop_state cdr_flags;
@@ -148,6 +149,13 @@ int cdr_reduce_features(const double* M, long ldm, const double* X, long ldx, in
 size_t cdr_gram_workspace_bytes(int T, int d);
 int cdr_gram(const double* X, long ldx, int T, int d, double* K, long ldk, void* workspace,
              size_t workspace_bytes, cdr_stream_t stream);
+/* K = X X' as a SYRK (tiles on and above the diagonal, mirrored; T^2 d flops; csrc/syrk.cu).
+ * part_index / part_count (0 / 1 for everything): only the upper-triangle tiles
+ * t = part_index (mod part_count) and their mirror images are written -- ranks of a process
+ * group deal the tiles this way and sum the zero-initialised matrices. */
+size_t cdr_syrk_workspace_bytes(int T, int d);
+int cdr_syrk(const double* X, long ldx, int T, int d, double* K, long ldk, int part_index,
+             int part_count, void* workspace, size_t workspace_bytes, cdr_stream_t stream);
 /* sum of squares of a T x d matrix (trace of the Gram, archetypal_analysis.py:552) */
 int cdr_frobenius_sq(const double* X, long ldx, int T, int d, double* out, void* workspace,
                      size_t workspace_bytes, cdr_stream_t stream);
@@ -342,6 +350,80 @@ int cdr_reduce_samples_allreduce(const cdr_peer_group* group, const double* Lp, 
                                  long sLt, const double* X, long ldx, int T, int T_min, int d,
                                  int k, const double* E, size_t out_offset, long ldo,
                                  const cdr_flags* flags, cdr_stream_t stream);
+
+/* ------------------------------------------------------------------ whole outer iterations
+ * One call enqueues a complete outer (alternating) iteration on `stream`; the convergence and
+ * monotonicity tests run on the device (cdr_loop_state), so a host loop -- or a CUDA graph
+ * replayed N times -- only has to look at `state->done` every now and then.  These are the
+ * entry points a non-Python binder needs in place of the reference's loops
+ *   _iterate_gpnh_convex_coding  (gpnh_convex_coding.py:282-402)
+ *   _iterate_aa                  (archetypal_analysis.py:534-670).
+ * All pointers are device pointers; X, WT, C ... are padded (leading dimension a multiple of
+ * CDR_LD_ALIGN, padding zero).  The `state` block must have been initialised by the caller
+ * (tolerance, max_iterations, stopping_rule, require_monotone, trace_data; everything else
+ * zero).  Protocol:   prepare_enqueue once, then iterate_enqueue until state->done.
+ */
+typedef struct cdr_gpnh_problem {
+    const double* X;      /* T x d data, leading dimension ldx */
+    long ldx;
+    int T, d, k;
+    int T_total;          /* = T (single GPU) */
+    double lambda_W;
+    double* Z;            /* T x k weights, dense, updated in place */
+    double* WT;           /* k x ldx: the dictionary transposed (gpnh_convex_coding.py:226), updated in place */
+    double* XWt;          /* k x ldt scratch: (X W)' */
+    long ldt;             /* >= T, multiple of CDR_LD_ALIGN */
+    double* ZtZ;          /* k x k statistics, maintained across iterations */
+    double* XWtZ;
+    double* WtW;
+    double* REG;          /* k x k pairwise ||w_i - w_j||^2 (lambda_W != 0) */
+    double* P;            /* k x k solve matrix of the next dictionary step */
+    cdr_loop_state* state;
+    double* cost_deltas;  /* max_iterations doubles */
+    cdr_spg_params weights_params;
+    void* workspace;      /* cdr_gpnh_workspace_bytes(T, d, k) */
+    size_t workspace_bytes;
+} cdr_gpnh_problem;
+
+size_t cdr_gpnh_workspace_bytes(int T, int d, int k);
+/* gpnh_convex_coding.py:292-314: products and cost of the initial factors, then the start of
+ * the first iteration (old_cost, solve matrix P). */
+int cdr_gpnh_prepare_enqueue(const cdr_gpnh_problem* problem, cdr_stream_t stream);
+/* gpnh_convex_coding.py:339-399: dictionary update, weights update, both cost checks, stopping
+ * rule, start of the next iteration.  For k <= 16 at streaming shapes
+ * (cdr_gpnh_fused_applicable) this is three kernels: W' = P Z'X (reduce over samples, solve in
+ * the epilogue), X W as per-strip partials with W'W as a by-product of the same pass, and the
+ * per-sample QPs with the statistics Z'Z, tr(W'X'Z), both cost checks and the next solve
+ * matrix formed by the last CTA to finish; XWt / XWtZ are then scratch of
+ * cdr_gpnh_prepare_enqueue only.  Other shapes run the general kernel sequence. */
+int cdr_gpnh_iterate_enqueue(const cdr_gpnh_problem* problem, cdr_stream_t stream);
+int cdr_gpnh_fused_applicable(int T, int d, int k); /* host-only: 1 = three-kernel path */
+
+/* Archetypal analysis in feature space (archetypal_analysis.py:534-670), delta = 0 (no scale
+ * factor update), dictionary SPG with 1 <= max_iterations <= 8 inner iterations (longer inner
+ * loops need the host to look at the state between bursts: use the cdr_aa_spg_* pieces). */
+typedef struct cdr_aa_problem {
+    const double* X;      /* T x d data, leading dimension ldx */
+    long ldx;
+    int T, d;
+    cdr_aa_buffers buf;   /* C, G, D, CK, DK, KZt (k x ldt), alpha, k x k statistics, state */
+    double* Z;            /* T x k weights, dense, updated in place */
+    double* tmp_kd;       /* k x ldx scratch: D X, Z'X */
+    cdr_spg_params dictionary_params; /* defaults spg.py:46-51 */
+    cdr_spg_params weights_params;    /* defaults spg.py:287-291 */
+    void* workspace;      /* cdr_aa_workspace_bytes(T, d, k) */
+    size_t workspace_bytes;
+} cdr_aa_problem;
+
+size_t cdr_aa_workspace_bytes(int T, int d, int k);
+/* archetypal_analysis.py:541-556: C X X', X X' Z, Z'Z, C X X' C', the initial cost; then the
+ * projection of the start that spg() applies first (spg.py:146-148) and old_cost. */
+int cdr_aa_prepare_enqueue(const cdr_aa_problem* problem, cdr_stream_t stream);
+/* archetypal_analysis.py:586-663: dictionary SPG step(s), weights update, both cost checks,
+ * stopping rule.  With one inner iteration and k <= 16 at streaming shapes
+ * (cdr_aa_fused_applicable) this is eight kernels, see csrc/iterate_aa.cu. */
+int cdr_aa_iterate_enqueue(const cdr_aa_problem* problem, cdr_stream_t stream);
+int cdr_aa_fused_applicable(int T, int d, int k, int dictionary_max_iterations);
 
 #ifdef __cplusplus
 }

@@ -52,7 +52,7 @@ class LoopState(ctypes.Structure):
                 ('a0', ctypes.c_double), ('a1', ctypes.c_double),
                 ('beta', ctypes.c_double), ('res2', ctypes.c_double),
                 ('resinf', ctypes.c_double), ('penalty', ctypes.c_double),
-                ('f_mem', ctypes.c_double * MAX_MEMORY)]
+                ('f_mem', ctypes.c_double * MAX_MEMORY), ('tickets', ctypes.c_uint * 4)]
 
 
 class SmallGramDesc(ctypes.Structure):
@@ -77,6 +77,30 @@ class AaBuffers(ctypes.Structure):
                 ('cost_deltas', ctypes.c_void_p),
                 ('k', ctypes.c_int), ('T', ctypes.c_int), ('ldt', ctypes.c_long),
                 ('grad_scale', ctypes.c_double), ('cost_scale', ctypes.c_double)]
+
+
+class GpnhProblem(ctypes.Structure):
+    """Mirror of ``cdr_gpnh_problem``."""
+
+    _fields_ = [('X', ctypes.c_void_p), ('ldx', ctypes.c_long),
+                ('T', ctypes.c_int), ('d', ctypes.c_int), ('k', ctypes.c_int),
+                ('T_total', ctypes.c_int), ('lambda_W', ctypes.c_double),
+                ('Z', ctypes.c_void_p), ('WT', ctypes.c_void_p), ('XWt', ctypes.c_void_p),
+                ('ldt', ctypes.c_long), ('ZtZ', ctypes.c_void_p), ('XWtZ', ctypes.c_void_p),
+                ('WtW', ctypes.c_void_p), ('REG', ctypes.c_void_p), ('P', ctypes.c_void_p),
+                ('state', ctypes.c_void_p), ('cost_deltas', ctypes.c_void_p),
+                ('weights_params', SpgParams), ('workspace', ctypes.c_void_p),
+                ('workspace_bytes', ctypes.c_size_t)]
+
+
+class AaProblem(ctypes.Structure):
+    """Mirror of ``cdr_aa_problem``."""
+
+    _fields_ = [('X', ctypes.c_void_p), ('ldx', ctypes.c_long),
+                ('T', ctypes.c_int), ('d', ctypes.c_int), ('buf', AaBuffers),
+                ('Z', ctypes.c_void_p), ('tmp_kd', ctypes.c_void_p),
+                ('dictionary_params', SpgParams), ('weights_params', SpgParams),
+                ('workspace', ctypes.c_void_p), ('workspace_bytes', ctypes.c_size_t)]
 
 
 MAX_PEERS = 8
@@ -110,6 +134,8 @@ SIGNATURES = {
     'cdr_reduce_features': (_i, [_vp, _l, _vp, _l, _i, _i, _i, _vp, _l, _vp, _sz, _vp, _vp]),
     'cdr_gram_workspace_bytes': (_sz, [_i, _i]),
     'cdr_gram': (_i, [_vp, _l, _i, _i, _vp, _l, _vp, _sz, _vp]),
+    'cdr_syrk_workspace_bytes': (_sz, [_i, _i]),
+    'cdr_syrk': (_i, [_vp, _l, _i, _i, _vp, _l, _i, _i, _vp, _sz, _vp]),
     'cdr_frobenius_workspace_bytes': (_sz, []),
     'cdr_frobenius_sq': (_i, [_vp, _l, _i, _i, _vp, _vp, _sz, _vp]),
     'cdr_sum_vector': (_i, [_vp, _i, _vp, _vp]),
@@ -128,6 +154,14 @@ SIGNATURES = {
     'cdr_aa_spg_update': (_i, [ctypes.POINTER(AaBuffers), ctypes.POINTER(SpgParams), _i, _vp]),
     'cdr_aa_cost_check': (_i, [ctypes.POINTER(AaBuffers), _i, _i, _vp]),
     'cdr_gpnh_cost_check': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _i, _i, _vp]),
+    'cdr_gpnh_workspace_bytes': (_sz, [_i, _i, _i]),
+    'cdr_gpnh_prepare_enqueue': (_i, [ctypes.POINTER(GpnhProblem), _vp]),
+    'cdr_gpnh_iterate_enqueue': (_i, [ctypes.POINTER(GpnhProblem), _vp]),
+    'cdr_gpnh_fused_applicable': (_i, [_i, _i, _i]),
+    'cdr_aa_workspace_bytes': (_sz, [_i, _i, _i]),
+    'cdr_aa_prepare_enqueue': (_i, [ctypes.POINTER(AaProblem), _vp]),
+    'cdr_aa_iterate_enqueue': (_i, [ctypes.POINTER(AaProblem), _vp]),
+    'cdr_aa_fused_applicable': (_i, [_i, _i, _i, _i]),
     'cdr_dissimilarity_from_gram': (_i, [_vp, _l, _i, _vp, _l, _vp]),
     'cdr_furthest_sum_workspace_bytes': (_sz, [_i, _i, _i]),
     'cdr_furthest_sum': (_i, [_vp, _l, _i, _i, _i, _vp, _i, _i, _vp, _vp, _sz, _vp]),
@@ -384,36 +418,38 @@ def frobenius_sq(X, T, d):
     return out
 
 
-GRAM_SLAB_ROWS = 64      # cdr_gram forms K in slabs of this many rows (stream_gemm.cu)
-
-
 def gram(X, T, d, comm=None):
-    """K = X X' as a padded (T, round_up(T)) device matrix.
+    """K = X X' as a padded (T, round_up(T)) device matrix (SYRK: upper-triangle tiles,
+    mirrored; csrc/syrk.cu).
 
-    With a process group every rank holds the same X (all T rows): the 64-row slabs of K are
-    dealt round-robin to the ranks, each slab computed by the very call ``cdr_gram`` makes for
-    it, and summed into place by one all-reduce (zeros elsewhere, so the sum is exact and K
-    is bit-identical to the single-GPU result).
+    With a process group every rank holds the same X (all T rows): the upper-triangle tiles
+    are dealt round-robin to the ranks and summed into place by one all-reduce (zeros
+    elsewhere, so the sum is exact and K is bit-identical to the single-GPU result).
     """
+    torch = require_cuda()
+    lib = library()
+    K = torch.zeros((T, round_up(T)), dtype=torch.float64, device='cuda')
+    nbytes = lib.cdr_syrk_workspace_bytes(T, d)
+    ws = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device='cuda')
+    sharded = comm is not None and comm.enabled
+    index, count = (comm.rank, comm.world) if sharded else (0, 1)
+    check(lib.cdr_syrk(ptr(X), X.stride(0), T, d, ptr(K), K.stride(0), index, count, ptr(ws),
+                       ws.numel() * 8, stream_ptr()), 'cdr_syrk')
+    if sharded:
+        comm.allreduce_sum(K)
+    return K
+
+
+def gram_slabs(X, T, d):
+    """K = X X' by repeated 64-row feature reductions (cdr_gram; the round-1 path, kept as a
+    cross-check of the SYRK kernel)."""
     torch = require_cuda()
     lib = library()
     K = torch.zeros((T, round_up(T)), dtype=torch.float64, device='cuda')
     nbytes = lib.cdr_gram_workspace_bytes(T, d)
     ws = torch.zeros(nbytes // 8 + 1, dtype=torch.float64, device='cuda')
-    if comm is None or not comm.enabled:
-        check(lib.cdr_gram(ptr(X), X.stride(0), T, d, ptr(K), K.stride(0), ptr(ws),
-                           ws.numel() * 8, stream_ptr()), 'cdr_gram')
-        return K
-    ldx, ldk = X.stride(0), K.stride(0)
-    for slab, r0 in enumerate(range(0, T, GRAM_SLAB_ROWS)):
-        if slab % comm.world != comm.rank:
-            continue
-        rows = min(GRAM_SLAB_ROWS, T - r0)
-        check(lib.cdr_reduce_features(
-            X.data_ptr() + 8 * r0 * ldx, ldx, X.data_ptr(), ldx, T, d, rows,
-            K.data_ptr() + 8 * r0 * ldk, ldk, ptr(ws), ws.numel() * 8, None, stream_ptr()),
-            'cdr_reduce_features')
-    comm.allreduce_sum(K)
+    check(lib.cdr_gram(ptr(X), X.stride(0), T, d, ptr(K), K.stride(0), ptr(ws),
+                       ws.numel() * 8, stream_ptr()), 'cdr_gram')
     return K
 
 

@@ -224,6 +224,18 @@ class Comm:
         self._dist.broadcast_object_list(box, src=src, group=self.group)
         return box[0]
 
+    def sync_random_state(self, rng):
+        """Make rank 0's generator state the state of ``rng`` on every rank (collective).
+
+        Sample-sharded fits draw the full-size initial factors on every rank and rely on the
+        replicas being bit-identical; with ``random_state=None`` each rank would otherwise
+        seed from OS entropy and the replicas -- and with them the device-side `done` flags
+        and the collective sequences -- would silently diverge.  A no-op when every rank was
+        given the same seed."""
+        if self.enabled:
+            rng.set_state(self.broadcast_object(rng.get_state(), src=0))
+        return rng
+
     def allgather_rows(self, local_np):
         """Gather NumPy row blocks of all ranks (used for the final weights)."""
         if not self.enabled:

@@ -32,6 +32,8 @@ _STAGES = {1: 'scale factors', 2: 'dictionary', 3: 'weights'}
 
 # inner SPG iterations up to which the whole outer iteration is captured in one graph
 _MAX_UNROLLED_SPG = 8
+# csrc/aa_steps.cu kRowMaxT: a dictionary row (length T) is staged in shared memory
+MAX_SAMPLES = 26000
 
 
 def _check_init_weights(weights, shape, whom):
@@ -88,6 +90,11 @@ class _AaEngine:
         if k > be.MAX_COMPONENTS:
             raise ValueError('n_components > %d is not supported by the B200 build'
                              % be.MAX_COMPONENTS)
+        if T > MAX_SAMPLES:
+            raise ValueError('archetypal analysis of more than %d samples (total, also when '
+                             'sharded) is not supported by the B200 build: the dictionary row '
+                             'kernels stage one k x T row in shared memory; got %d'
+                             % (MAX_SAMPLES, T))
         self.d = data.shape[1]
         self.delta = delta
         self.update_weights = update_weights
@@ -153,6 +160,21 @@ class _AaEngine:
             self.G01.data_ptr(), self.G11.data_ptr(), self.row_scratch.data_ptr(),
             self.state.ptr, self.state.cost_deltas.data_ptr(), k, T, ldt, grad_scale, 1.0 / k)
         self._first_dictionary_update = True
+        # single-GPU feature-space fits with a short inner SPG loop and no scale-factor update
+        # run behind the C entry points cdr_aa_prepare_enqueue / cdr_aa_iterate_enqueue
+        # (eight kernels per outer iteration at streaming shapes with one inner iteration)
+        self.c_loop = (mode == 'feature' and not self.comm.enabled and update_weights and
+                       update_dictionary and not (update_scale_factors and delta != 0) and
+                       1 <= self.d_params.max_iterations <= _MAX_UNROLLED_SPG)
+        if self.c_loop:
+            nbytes = self.lib.cdr_aa_workspace_bytes(T, self.d, k)
+            self.c_ws = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device='cuda')
+            self.problem = be.AaProblem(
+                self.X.data_ptr(), self.ldx, T, self.d, self.buf, self.Z.data_ptr(),
+                self.tmp_kd.data_ptr(), self.d_params, self.w_params, self.c_ws.data_ptr(),
+                self.c_ws.numel() * 8)
+            self.fused = bool(self.lib.cdr_aa_fused_applicable(
+                T, self.d, k, self.d_params.max_iterations))
 
     # -- products with K ----------------------------------------------------
     def _samples_sum(self, L, sLi, sLt, flags):
@@ -218,6 +240,11 @@ class _AaEngine:
         self.comm.allreduce_sum(self.ZtZ)
 
     def initial_cost(self):
+        if self.c_loop:
+            be.check(self.lib.cdr_aa_prepare_enqueue(ctypes.byref(self.problem),
+                                                     be.stream_ptr()), 'cdr_aa_prepare_enqueue')
+            self._first_dictionary_update = False
+            return
         self.precompute()
         self._cost_check(0, False)
 
@@ -309,6 +336,10 @@ class _AaEngine:
         self._cost_check(1, False)
 
     def iteration(self):
+        if self.c_loop:
+            be.check(self.lib.cdr_aa_iterate_enqueue(ctypes.byref(self.problem),
+                                                     be.stream_ptr()), 'cdr_aa_iterate_enqueue')
+            return
         be.check(self.lib.cdr_loop_begin(self.state.ptr, be.stream_ptr()), 'cdr_loop_begin')
         if self.update_scale_factors and self.delta != 0:
             self.scale_factors_step()
@@ -378,6 +409,8 @@ class _AaEngine:
             warnings.warn('step size below tolerance in SPG line search', UserWarning)
         if st.spg_warnings & 2:
             warnings.warn('maximum number of function evaluations exceeded in SPG', UserWarning)
+        if st.spg_warnings & 4:
+            warnings.warn('maximum number of iterations exceeded in SPG', UserWarning)
         self.cost = st.cost
         self.n_iter = st.n_iter - 1            # 0-based loop index, like the reference
         self.avg_time_per_iter = elapsed / max(st.n_iter, 1)
@@ -852,6 +885,7 @@ class ArchetypalAnalysis(_AaBase):
         row0 = 0
         if sharded:
             row0, n_samples = comm.local_rows(n_samples)
+            comm.sync_random_state(self.random_state)      # rank 0 is authoritative
         self._check_params(data.shape[1])
         data64 = np.ascontiguousarray(data, dtype=np.float64)
         Xd = be.to_device_padded(data64)

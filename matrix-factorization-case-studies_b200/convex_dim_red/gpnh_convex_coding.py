@@ -9,6 +9,7 @@ and monotonicity tests run on the device, and one outer iteration is replayed
 from a CUDA graph.
 """
 
+import ctypes
 import numbers
 import time
 import warnings
@@ -97,6 +98,19 @@ class _GpnhEngine:
         self.comm.allreduce_max(t_min)
         self.T_min = -int(t_min.item())      # smallest local T: keeps kernel choices identical
         self.lib = be.library()
+        # single-GPU full iterations run behind the C entry points cdr_gpnh_prepare_enqueue /
+        # cdr_gpnh_iterate_enqueue (three kernels per iteration at streaming shapes, k <= 16)
+        self.c_loop = (not self.comm.enabled) and update_dictionary and update_weights
+        if self.c_loop:
+            nbytes = self.lib.cdr_gpnh_workspace_bytes(T, d, k)
+            self.c_ws = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device='cuda')
+            self.problem = be.GpnhProblem(
+                self.X.data_ptr(), self.ldx, T, d, k, T, self.lambda_W, self.Z.data_ptr(),
+                self.WT.data_ptr(), self.XWt.data_ptr(), self.ldt, self.ZtZ.data_ptr(),
+                self.XWtZ.data_ptr(), self.WtW.data_ptr(), self.REG.data_ptr(),
+                self.P.data_ptr(), self.state.ptr, self.state.cost_deltas.data_ptr(),
+                self.params, self.c_ws.data_ptr(), self.c_ws.numel() * 8)
+            self.fused = bool(self.lib.cdr_gpnh_fused_applicable(T, d, k))
 
     # -- small products -----------------------------------------------------
     def _desc_ZtZ(self):
@@ -127,6 +141,11 @@ class _GpnhEngine:
     # -- pieces of the loop -------------------------------------------------
     def initial_cost(self):
         """gpnh_convex_coding.py:292-314."""
+        if self.c_loop:
+            be.check(self.lib.cdr_gpnh_prepare_enqueue(ctypes.byref(self.problem),
+                                                       be.stream_ptr()),
+                     'cdr_gpnh_prepare_enqueue')
+            return
         flags = self.state.ptr
         be.reduce_features(self.WT, self.X, self.T, self.d, self.k, self.XWt, self.ws, flags)
         descs = [self._desc_ZtZ(), self._desc_WtW(), self._desc_XWtZ()]
@@ -186,6 +205,11 @@ class _GpnhEngine:
             self._cost_check(stage, end, False)
 
     def iteration(self):
+        if self.c_loop:
+            be.check(self.lib.cdr_gpnh_iterate_enqueue(ctypes.byref(self.problem),
+                                                       be.stream_ptr()),
+                     'cdr_gpnh_iterate_enqueue')
+            return
         be.check(self.lib.cdr_loop_begin(self.state.ptr, be.stream_ptr()), 'cdr_loop_begin')
         if self.update_dictionary:
             self.dictionary_step(end=not self.update_weights)
@@ -497,6 +521,7 @@ class GPNHConvexCoding():
         row0 = 0
         if sharded:
             row0, n_samples = comm.local_rows(n_samples)
+            comm.sync_random_state(self.random_state)      # rank 0 is authoritative
             kwargs = dict(kwargs, n_samples=n_samples)
         self._check_params(n_features)
         k = self.n_components

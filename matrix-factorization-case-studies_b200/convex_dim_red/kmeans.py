@@ -401,39 +401,89 @@ def _assign_only(X, centres):
     return labels.cpu().numpy(), None, None, None
 
 
-def gap_statistic(X, n_clusters, n_trials=100, n_init=10, reference='pca',
-                  random_state=None, **kwargs):
-    """Gap statistic of Tibshirani et al. around this module's k-means
-    (reference kmeans.py:81-108; model selection, outside the alternating-update path).
+def _calculate_uniform_reference_wk(X, n_clusters, n_init=10, n_jobs=None, random_state=None):
+    """Within-cluster dispersion of one uniform reference data set (reference kmeans.py:18-34):
+    same RNG draws in the same order -- the box sample, then the k-means++ seeding of the
+    ``n_init`` restarts -- with this module's k-means in place of scikit-learn's.  ``n_jobs``
+    is accepted for signature compatibility (the Lloyd iterations run on the GPU)."""
+    rng = check_random_state(random_state)
+    n_samples, n_features = X.shape
+    feature_min = np.broadcast_to(np.min(X, axis=0), (n_samples, n_features))
+    feature_max = np.broadcast_to(np.max(X, axis=0), (n_samples, n_features))
+    random_data = ((feature_max - feature_min) * rng.uniform(
+        size=(n_samples, n_features)) + feature_min)
+    kmeans = KMeans(n_clusters=n_clusters, init='k-means++', n_init=n_init,
+                    random_state=rng).fit(random_data)
+    return kmeans.inertia_
 
-    Returns ``(gap, standard_error)``.  Reference data are drawn uniformly from the
-    bounding box of X ('uniform') or of X rotated onto its principal axes ('pca').
+
+def _calculate_pca_reference_wk(X, n_clusters, n_init=10, n_components=100, n_iter=10,
+                                n_jobs=None, random_state=None):
+    """As above with the box aligned to the leading right singular vectors of X (reference
+    kmeans.py:37-64; the randomised ``TruncatedSVD`` is scikit-learn's, as in the reference)."""
+    from sklearn.decomposition import TruncatedSVD
+    rng = check_random_state(random_state)
+    n_samples = X.shape[0]
+    svd = TruncatedSVD(n_components=n_components, n_iter=n_iter, random_state=rng)
+    svd.fit(X)
+    Vh = svd.components_
+    Xp = np.dot(X, np.transpose(Vh))
+    feature_min = np.broadcast_to(np.min(Xp, axis=0), (n_samples, n_components))
+    feature_max = np.broadcast_to(np.max(Xp, axis=0), (n_samples, n_components))
+    random_data = ((feature_max - feature_min) * rng.uniform(
+        size=(n_samples, n_components)) + feature_min)
+    random_data = np.dot(random_data, Vh)
+    kmeans = KMeans(n_clusters=n_clusters, init='k-means++', n_init=n_init,
+                    random_state=rng).fit(random_data)
+    return kmeans.inertia_
+
+
+def _calculate_reference_wk(X, n_components, reference='uniform', random_state=None):
+    if reference == 'uniform':
+        return _calculate_uniform_reference_wk(X, n_components, random_state=random_state)
+    if reference == 'pca':
+        return _calculate_pca_reference_wk(X, n_components, random_state=random_state)
+    raise ValueError("unrecognized reference distribution '%s'" % reference)
+
+
+def gap_statistic(X, Wk, n_components, n_trials=100, reference='uniform', n_jobs=1,
+                  random_state=None):
+    """Calculate gap statistic for k-means clustering (reference kmeans.py:81-108).
+
+    ``Wk`` is the inertia of the caller's own fit (the drivers pass ``model.inertia_``,
+    bin/run_hadisst_kmeans.py:133); returns ``(gap, sk)`` with
+    ``gap = mean(log Wk_ref) - log Wk``.  One seed per trial is drawn first, exactly as the
+    reference does, so the reference data sets do not depend on the trial order.  ``n_jobs``
+    is accepted for compatibility: the trials run one after the other on the GPU.
     """
     rng = check_random_state(random_state)
     X = np.ascontiguousarray(X, dtype=np.float64)
 
-    def dispersion(data):
-        model = KMeans(n_clusters=n_clusters, init='random', n_init=n_init, random_state=rng,
-                       **kwargs).fit(data)
-        return np.log(model.inertia_)
+    random_seeds = []
+    for _ in range(n_trials):
+        has_seed_already = True
+        while has_seed_already:
+            seed = rng.randint(np.iinfo(np.int32).max)
+            if seed not in random_seeds:
+                random_seeds.append(seed)
+                has_seed_already = False
 
-    if reference not in ('uniform', 'pca'):
-        raise ValueError("invalid reference distribution '%s'" % reference)
-    log_w = dispersion(X)
-    centred = X - X.mean(axis=0)
-    if reference == 'pca':
-        _, _, vt = np.linalg.svd(centred, full_matrices=False)
-        rotated = centred.dot(vt.T)
-    else:
-        vt = None
-        rotated = X
-    lo, hi = rotated.min(axis=0), rotated.max(axis=0)
-    ref_log_w = np.empty(n_trials)
-    for i in range(n_trials):
-        sample = rng.uniform(lo, hi, size=rotated.shape)
-        if vt is not None:
-            sample = sample.dot(vt) + X.mean(axis=0)
-        ref_log_w[i] = dispersion(sample)
-    gap = ref_log_w.mean() - log_w
-    sk = np.sqrt(1.0 + 1.0 / n_trials) * ref_log_w.std()
+    Wk_ref = np.array([_calculate_reference_wk(X, n_components, reference=reference,
+                                               random_state=random_seeds[i])
+                       for i in range(n_trials)])
+    lnWk_ref = np.log(Wk_ref)
+    sk = np.std(lnWk_ref) * np.sqrt(1 + 1.0 / n_trials)
+    gap = lnWk_ref.mean() - np.log(Wk)
     return gap, sk
+
+
+def gap_statistic_fit(X, n_clusters, n_trials=100, n_init=10, reference='uniform',
+                      random_state=None):
+    """Convenience form (not in the reference): fits k-means on ``X`` itself and returns
+    ``gap_statistic(X, inertia, n_clusters, ...)``."""
+    rng = check_random_state(random_state)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    model = KMeans(n_clusters=n_clusters, init='k-means++', n_init=n_init,
+                   random_state=rng).fit(X)
+    return gap_statistic(X, model.inertia_, n_clusters, n_trials=n_trials, reference=reference,
+                         random_state=rng)

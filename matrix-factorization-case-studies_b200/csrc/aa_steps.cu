@@ -77,7 +77,8 @@ __global__ void aa_spg_f0_kernel(cdr_aa_buffers b, cdr_spg_params p)
     st->spg_iter = 0;
     st->spg_feval = 1;
     st->spg_active = (p.max_iterations > 0) ? 1 : 0;
-    st->spg_warnings = 0;
+    // spg_warnings is sticky over the outer iterations of a fit (the reference warns on every
+    // occurrence; the host reports each kind once at the end)
     for (int i = 0; i < CDR_MAX_MEMORY; ++i) st->f_mem[i] = 0.0;      // zeros: spg.py:153
     if (p.alpha0 > 0.0) {
         // explicit alpha0 (spg.py:151); the reference uses it unclamped when not None
@@ -229,6 +230,9 @@ __global__ void aa_spg_linesearch_kernel(cdr_aa_buffers b, cdr_spg_params p)
             break;
         }
     }
+    // the last inner iteration: the limit is reached (spg.py:277-281; the convergence test of
+    // that iteration is not evaluated when its result could only suppress this warning)
+    if (st->spg_iter + 1 >= p.max_iterations) st->spg_warnings |= 4;
     st->lam = lam;
     st->f_new = f_new;
     st->delta = delta;

@@ -149,9 +149,23 @@ static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 int run_reduce_samples_tma(const double* Lp, long sLi, long sLt, const double* X, long ldx, int T,
                            int d, int k, const double* E, double* out, long ldo,
                            const cdr_flags* flags, cudaStream_t stream);
+// Optional by-product of the strip-owned reduce over features (the fused GPNH iteration,
+// iterate.cu): the k x k Gram matrix M M' of the operand itself.  The B fragments of a strip
+// serve as both DMMA operands (a fragment value M[lc][f(lr)] is at once A[lc][lr] and
+// B[lr][lc]); the per-strip results go to part[strip][KP * KP] and the last CTA to finish sums
+// them in strip order into out.
+struct StripGram {
+    double* part;            // nullptr: no by-product
+    double* out;             // k x k, row-major
+    unsigned int* ticket;    // zero before the first launch; left at zero
+};
+// out == nullptr: no finalize launch, the caller consumes the per-strip partials
+// workspace[strip][t][KP] itself (KP = 8 or 16; geometry from features_strip_geometry)
 int run_reduce_features_tma(const double* M, long ldm, const double* X, long ldx, int T, int d,
                             int k, double* out, long ldo, void* workspace, size_t workspace_bytes,
-                            const cdr_flags* flags, cudaStream_t stream);
+                            const cdr_flags* flags, cudaStream_t stream,
+                            const StripGram* gram = nullptr);
+bool features_strip_geometry(int T, int d, int k, int* TC, int* nstrips);
 size_t reduce_features_tma_workspace_bytes(int T, int d, int k);
 void tma_stream_plan(int T, int d, int k, int with_epilogue, int* out);
 int run_reduce_samples_exchange(const cdr_peer_group& g, size_t out_offset, const double* Lp,

@@ -1,0 +1,655 @@
+// Whole outer iterations of archetypal analysis behind one C call
+// (cdr_aa_prepare_enqueue / cdr_aa_iterate_enqueue).
+//
+// The reference's loop `_iterate_aa` (archetypal_analysis.py:534-670) is, per outer iteration:
+// dictionary update by the generic spg() with Python callbacks (:324-341, spg.py:46-283; the
+// drivers run it with max_iterations=1, bin/run_hadisst_aa.py:160-166), recomputes of C X,
+// C X X', C X X' C' (:618-621), cost check, per-sample QPs (:636), recomputes of Z'Z, X'Z,
+// X X'Z (:640-643), cost check.  With one inner SPG iteration, feature-space data and k <= 16
+// at streaming shapes that is eight kernels here:
+//
+//   1. aa_head_kernel (one CTA per dictionary row, one grid barrier): x = P(C) (spg.py:148),
+//      the linear trace term, df(x), the first step length 1 / max|P(x - g) - x| (spg.py:178-189),
+//      d = P(x - alpha g) - x and the row partials of <d,g>, <d,d> (spg.py:191-206)
+//   2. reduce over samples   D X                        (stream_tma.cu)
+//   3. reduce over features  (D X) X' as per-strip partials
+//   4. aa_finalize_ls_kernel: D K = sum of the strip partials, and per 32-sample block the
+//      k x k products CK C', CK D', DK D'; the last CTA sums them in fixed order, evaluates
+//      f(x) (spg.py:156), runs the non-monotone Armijo search on scalars (spg.py:196-229: with
+//      CK = C K maintained, f(x + lam d) is a quadratic in lam), forms C K C' of the accepted
+//      point and applies the cost check after the dictionary update (:623-630)
+//   5. aa_weights_fused_kernel: x += lam d, CK += lam DK for the sample's column, its QP
+//      (:344-366), and the statistics z z', tr(C K Z); the last CTA sums them, applies the cost
+//      check after the weights update and the stopping rule (:645-663) and starts the next
+//      iteration
+//   6.-8. (K Z)' = X (X' Z): reduce over samples, reduce over features + finalize (:641-642)
+//
+// Other configurations (more inner SPG iterations, k > 16, small or Gram-space problems) run
+// the general kernel sequence of aa_steps.cu.  All reductions have a fixed order.
+#include "fused_weights.cuh"
+#include "small_solve.cuh"
+
+namespace cdr {
+
+// slots of row_scratch (each k doubles); must match aa_steps.cu
+enum { RS_A0 = 0, RS_ROWMAX = 1, RS_DELTA = 2, RS_DD = 3, RS_A1 = 4, RS_BETA = 5, RS_R2 = 6, RS_RINF = 7 };
+
+constexpr int kAaRowMaxT = 26000;      // aa_steps.cu: rows are staged in shared memory
+
+// gradient entry (j, t):  s_g * (sum_i a_j a_i ZtZ[j][i] CK[i][t] - a_j KZt[j][t])
+__device__ __forceinline__ double aa_grad_entry(const cdr_aa_buffers& b, const double* coef, int j, int t)
+{
+    double s = 0.0;
+    for (int i = 0; i < b.k; ++i) s = fma(coef[i], b.CK[(long)i * b.ldt + t], s);
+    return b.grad_scale * (s - b.alpha[j] * b.KZt[(long)j * b.ldt + t]);
+}
+
+// ---------------------------------------------------------------------- kernel 1
+__global__ void __launch_bounds__(1024) aa_head_kernel(cdr_aa_buffers b, cdr_spg_params p)
+{
+    cdr_loop_state* st = b.state;
+    if (is_done(st)) return;
+    extern __shared__ double sm[];
+    double* scratch = sm;
+    double* coef = sm + 64;
+    double* work = sm + 64 + CDR_MAX_COMPONENTS;
+    const int j = blockIdx.x, k = b.k, T = b.T;
+    double* crow = b.C + (long)j * b.ldt;
+    double* grow = b.G + (long)j * b.ldt;
+    double* drow = b.D + (long)j * b.ldt;
+    const double* kz = b.KZt + (long)j * b.ldt;
+
+    // x = project(x0) (spg.py:146-148) and the linear trace term a0 = a_j <x, (K Z)_j>
+    for (int t = threadIdx.x; t < T; t += blockDim.x) work[t] = crow[t];
+    for (int i = threadIdx.x; i < k; i += blockDim.x)
+        coef[i] = b.alpha[j] * b.alpha[i] * b.ZtZ[j * k + i];
+    __syncthreads();
+    double th = block_simplex_threshold(work, 1, T, scratch);
+    double a0[1] = {0.0};
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        const double x = fmax(work[t] - th, 0.0);
+        crow[t] = x;
+        a0[0] = fma(x, kz[t], a0[0]);
+    }
+    block_sum<1>(a0, scratch);
+    if (threadIdx.x == 0) b.row_scratch[RS_A0 * k + j] = b.alpha[j] * a0[0];
+
+    // g = df(x) (spg.py:176); work = x - g
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        const double g = aa_grad_entry(b, coef, j, t);
+        grow[t] = g;
+        work[t] = crow[t] - g;
+    }
+    const bool explicit_alpha = p.alpha0 > 0.0;        // spg.py:151; used unclamped when given
+    if (!explicit_alpha) {
+        __syncthreads();
+        th = block_simplex_threshold(work, 1, T, scratch);
+        double m = 0.0;
+        for (int t = threadIdx.x; t < T; t += blockDim.x)
+            m = fmax(m, fabs(fmax(work[t] - th, 0.0) - crow[t]));
+        m = block_max(m, scratch);
+        if (threadIdx.x == 0) b.row_scratch[RS_ROWMAX * k + j] = m;
+    }
+
+    // ---- barrier over the k row CTAs (all resident: k <= 16).  The counter only grows:
+    // every launch adds exactly k, so the k arrivals of this launch see old values in
+    // [n k, (n + 1) k) and wait for (n + 1) k.
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int old = atomicAdd(&st->tickets[2], 1u);
+        const unsigned int target = (old / (unsigned int)k + 1u) * (unsigned int)k;
+        while (*((volatile unsigned int*)&st->tickets[2]) < target) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+
+    // first step length (spg.py:178-189)
+    double alpha;
+    if (explicit_alpha) {
+        alpha = p.alpha0;
+    } else {
+        double m = 0.0;
+        for (int i = 0; i < k; ++i) m = fmax(m, __ldcg(b.row_scratch + RS_ROWMAX * k + i));
+        alpha = (fabs(m) > 1e-12) ? 1.0 / m : 1.0;
+    }
+    if (j == 0 && threadIdx.x == 0) {
+        st->alpha = alpha;
+        st->spg_alpha_set = 1;
+    }
+
+    // d = P(x - alpha g) - x with <d,g>, <d,d> and the linear term along d (spg.py:191-206)
+    for (int t = threadIdx.x; t < T; t += blockDim.x) work[t] = crow[t] - alpha * grow[t];
+    __syncthreads();
+    th = block_simplex_threshold(work, 1, T, scratch);
+    double r[3] = {0.0, 0.0, 0.0};
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        const double d = fmax(work[t] - th, 0.0) - crow[t];
+        drow[t] = d;
+        r[0] = fma(d, grow[t], r[0]);
+        r[1] = fma(d, d, r[1]);
+        r[2] = fma(d, kz[t], r[2]);
+    }
+    block_sum<3>(r, scratch);
+    if (threadIdx.x == 0) {
+        b.row_scratch[RS_DELTA * k + j] = r[0];
+        b.row_scratch[RS_DD * k + j] = r[1];
+        b.row_scratch[RS_A1 * k + j] = b.alpha[j] * r[2];
+    }
+}
+
+// ---------------------------------------------------------------------- kernel 4
+constexpr int kFinTB = 32;             // samples per CTA
+constexpr int kFinThreads = 1024;
+
+template <int KT>
+__global__ void __launch_bounds__(kFinThreads)
+aa_finalize_ls_kernel(cdr_aa_buffers b, cdr_spg_params p, const double* __restrict__ part,
+                      int nstrips, double* cta_part)
+{
+    cdr_loop_state* st = b.state;
+    if (is_done(st)) return;
+    constexpr int KP = 8 * KT;
+    constexpr int PAIRS = KP / 2;
+    constexpr int ITEMS = kFinTB * PAIRS;              // 128 | 256
+    constexpr int GROUPS = kFinThreads / ITEMS;        // 8 | 4
+    constexpr int NOUT = 3 * KP * KP;                  // 192 | 768
+    constexpr int PH = (kFinThreads / NOUT) > 0 ? (kFinThreads / NOUT) : 1;   // 5 | 1
+    __shared__ double2 red[GROUPS][ITEMS];             // 16 KB; re-used by the tail
+    __shared__ double tiles[4][KP][kFinTB + 1];        // C, D, CK, DK
+    __shared__ int is_last;
+    const int k = b.k, T = b.T;
+    const long ldt = b.ldt;
+    const int t0 = blockIdx.x * kFinTB;
+
+    // ---- D K for this block of samples: sum of the per-strip partials, fixed order
+    {
+        const int item = threadIdx.x % ITEMS, grp = threadIdx.x / ITEMS;
+        const int tl = item / PAIRS, pr = item % PAIRS;
+        const int t = t0 + tl;
+        double s0 = 0.0, s1 = 0.0;
+        if (t < T) {
+            const double2* src = reinterpret_cast<const double2*>(part) + ((long)t * PAIRS + pr);
+            const long stride = (long)T * PAIRS;
+#pragma unroll 6
+            for (int s = grp; s < nstrips; s += GROUPS) {
+                const double2 v = __ldcg(src + (long)s * stride);
+                s0 += v.x;
+                s1 += v.y;
+            }
+        }
+        red[grp][item] = make_double2(s0, s1);
+        __syncthreads();
+        if (grp == 0) {
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int q = 0; q < GROUPS; ++q) {
+                a0 += red[q][item].x;
+                a1 += red[q][item].y;
+            }
+            const int j0 = 2 * pr;
+            const bool ok = t < T;
+            if (ok && j0 < k) b.DK[(long)j0 * ldt + t] = a0;
+            if (ok && j0 + 1 < k) b.DK[(long)(j0 + 1) * ldt + t] = a1;
+            tiles[3][j0][tl] = (ok && j0 < k) ? a0 : 0.0;
+            tiles[3][j0 + 1][tl] = (ok && j0 + 1 < k) ? a1 : 0.0;
+        }
+    }
+    for (int idx = threadIdx.x; idx < 3 * KP * kFinTB; idx += blockDim.x) {
+        const int a = idx / (KP * kFinTB), rem = idx % (KP * kFinTB);
+        const int i = rem / kFinTB, tl = rem % kFinTB;
+        const int t = t0 + tl;
+        const double* src = (a == 0) ? b.C : (a == 1) ? b.D : b.CK;
+        tiles[a][i][tl] = (i < k && t < T) ? src[(long)i * ldt + t] : 0.0;
+    }
+    __syncthreads();
+
+    // ---- k x k products over the block: CK C' (fresh C K C'), CK D', DK D'
+    for (int o = threadIdx.x; o < NOUT; o += blockDim.x) {
+        const int which = o / (KP * KP), i = (o % (KP * KP)) / KP, j = o % KP;
+        const double* left = (which == 2) ? tiles[3][i] : tiles[2][i];
+        const double* right = (which == 0) ? tiles[0][j] : tiles[1][j];
+        double s = 0.0;
+#pragma unroll
+        for (int tl = 0; tl < kFinTB; ++tl) s = fma(left[tl], right[tl], s);
+        __stcg(cta_part + (long)blockIdx.x * NOUT + o, s);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&st->tickets[3], 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+
+    // ------------------------------------------------------------------ last CTA
+    double* phs = reinterpret_cast<double*>(&red[0][0]);     // [PH][NOUT], then fin[NOUT]
+    double* fin = phs + PH * NOUT;
+    static_assert((PH + 1) * NOUT <= GROUPS * ITEMS * 2, "tail scratch does not fit");
+    {
+        const int nblk = gridDim.x;
+        const int e = (int)threadIdx.x % NOUT, ph = (int)threadIdx.x / NOUT;
+        if (ph < PH) {
+            const int n_mine = (nblk - ph + PH - 1) / PH;
+            double s = 0.0;
+            const double* src = cta_part + (long)ph * NOUT + e;
+#pragma unroll 4
+            for (int q = 0; q < n_mine; ++q) s += __ldcg(src + (long)q * PH * NOUT);
+            phs[ph * NOUT + e] = s;
+        }
+        __syncthreads();
+        for (int e2 = threadIdx.x; e2 < NOUT; e2 += blockDim.x) {
+            double s = phs[e2];
+#pragma unroll
+            for (int q = 1; q < PH; ++q) s += phs[q * NOUT + e2];
+            fin[e2] = s;
+        }
+        __syncthreads();
+    }
+    const double* G00 = fin;
+    const double* G01 = fin + KP * KP;
+    const double* G11 = fin + 2 * KP * KP;
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        // quadratic form coefficients  q(lam) = q0 + lam q1 + lam^2 q2  of tr(D Z'Z D . C K C')
+        double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+        for (int idx = lane; idx < k * k; idx += 32) {
+            const int i = idx / k, j = idx % k;
+            const double w = b.alpha[i] * b.alpha[j] * b.ZtZ[i * k + j];
+            q0 += w * G00[j * KP + i];
+            q1 += w * (G01[j * KP + i] + G01[i * KP + j]);
+            q2 += w * G11[j * KP + i];
+        }
+        q0 = warp_sum(q0);
+        q1 = warp_sum(q1);
+        q2 = warp_sum(q2);
+        double lam = 1.0;
+        if (lane == 0) {
+            double a0 = 0.0, delta = 0.0, dd = 0.0, a1 = 0.0;
+            for (int j = 0; j < k; ++j) {
+                a0 += b.row_scratch[RS_A0 * k + j];
+                delta += b.row_scratch[RS_DELTA * k + j];
+                dd += b.row_scratch[RS_DD * k + j];
+                a1 += b.row_scratch[RS_A1 * k + j];
+            }
+            const double tr = st->trace_data, sf = b.cost_scale;
+            // f(x) at the start of spg() (spg.py:153-157); the memory starts as zeros
+            const double f_old = 0.5 * (tr - 2.0 * a0 + q0) * sf;
+            double f_max = f_old;
+            for (int i = 1; i < p.memory; ++i) f_max = fmax(f_max, 0.0);
+            // non-monotone Armijo search (spg.py:196-229)
+            double f_new = 0.5 * (tr - 2.0 * (a0 + lam * a1) + (q0 + lam * q1 + lam * lam * q2)) * sf;
+            int feval = 2;
+            while (f_new > f_max + p.gamma * lam * delta) {
+                lam = spg_step_length(lam, delta, f_old, f_new, p.sigma_one, p.sigma_two);
+                f_new = 0.5 * (tr - 2.0 * (a0 + lam * a1) + (q0 + lam * q1 + lam * lam * q2)) * sf;
+                feval += 1;
+                if (fabs(lam) < p.lambda_min) {
+                    st->spg_warnings |= 1;
+                    break;
+                }
+            }
+            // one inner iteration: the iteration limit is reached without a convergence test
+            st->spg_warnings |= 4;
+            st->lam = lam;
+            st->f_old = f_old;
+            st->f_new = f_new;
+            st->delta = delta;
+            st->dd = dd;
+            st->a1 = a1;
+            st->a0 = a0 + lam * a1;
+            st->spg_iter = 1;
+            st->spg_feval = feval + 1;
+            // cost after the dictionary update (archetypal_analysis.py:623-630)
+            const double cost = 0.5 * (tr - 2.0 * (a0 + lam * a1) + (q0 + lam * q1 + lam * lam * q2)) /
+                                (double)T;
+            finish_sub_step(st, b.cost_deltas, cost, 2, 0);
+            st->tickets[3] = 0u;
+        }
+        lam = __shfl_sync(CDR_FULL_MASK, lam, 0);
+        // C K C' of the accepted point
+        for (int idx = lane; idx < k * k; idx += 32) {
+            const int i = idx / k, j = idx % k;
+            b.CKCt[idx] = G00[i * KP + j] + lam * (G01[i * KP + j] + G01[j * KP + i]) +
+                          lam * lam * G11[i * KP + j];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------- kernel 5
+struct AaWeightsArgs {
+    cdr_aa_buffers b;
+    double* Z;
+    double* cta_part;
+    int spw;
+    cdr_spg_params p;
+};
+
+template <int KPL>
+__global__ void __launch_bounds__(kFusedThreads) aa_weights_fused_kernel(AaWeightsArgs a)
+{
+    const cdr_aa_buffers& b = a.b;
+    cdr_loop_state* st = b.state;
+    if (is_done(st)) return;
+    constexpr int KP = 8 * KPL;
+    constexpr int NST = KP * KP + 2;
+    extern __shared__ double fsm[];
+    double* As = fsm;                               // KP x KP (KPL > 1)
+    double* wsum = fsm + (KPL > 1 ? KP * KP : 0);   // [kFusedWarps][NST]
+    double* fin = wsum + kFusedWarps * NST;         // 4 * NST
+
+    const int k = b.k, T = b.T;
+    const long ldt = b.ldt;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane & 7, q = lane >> 3;
+
+    // A' = D (C K C') D  (archetypal_analysis.py:384-385)
+    if constexpr (KPL > 1) {
+        for (int idx = threadIdx.x; idx < KP * KP; idx += blockDim.x) {
+            const int j = idx / KP, c = idx % KP;
+            As[idx] = (j < k && c < k) ? b.CKCt[(long)c * k + j] * b.alpha[c] * b.alpha[j] : 0.0;
+        }
+        __syncthreads();
+    }
+    double arow[8];
+    if constexpr (KPL == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            arow[j] = (g < k && j < k) ? b.CKCt[(long)g * k + j] * b.alpha[g] * b.alpha[j] : 0.0;
+    }
+
+    const int spw = a.spw;
+    const int t_raw = (blockIdx.x * kFusedWarps + warp) * spw + (q % spw);
+    const bool has_sample = t_raw < T;
+    const bool valid = (q < spw) && has_sample;
+    const long t = has_sample ? t_raw : (T - 1);
+    const double lam = st->lam;
+
+    // x <- x + lam d, C K <- C K + lam D K for this sample's column (spg.py:219; linearity
+    // of C -> C K), then the linear term b = -D (C K)[:, t]
+    double z0[KPL], x[KPL], bl[KPL], ck[KPL];
+    bool present[KPL];
+#pragma unroll
+    for (int r = 0; r < KPL; ++r) {
+        const int c = g * KPL + r;
+        present[r] = c < k;
+        if (present[r]) {
+            const long idx = (long)c * ldt + t;
+            const double cn = fma(lam, b.D[idx], b.C[idx]);
+            const double ckn = fma(lam, b.DK[idx], b.CK[idx]);
+            if (valid) {
+                b.C[idx] = cn;
+                b.CK[idx] = ckn;
+            }
+            ck[r] = b.alpha[c] * ckn;
+            bl[r] = -ck[r];
+            z0[r] = a.Z[t * k + c];
+        } else {
+            ck[r] = 0.0;
+            bl[r] = 0.0;
+            z0[r] = -INFINITY;
+        }
+    }
+
+    int n_iter = 0, n_feval = 0;
+    qp_solve<KPL>(As, arow, z0, bl, present, a.p, valid, g, x, n_iter, n_feval);
+
+    double tr_new = 0.0;
+    if (valid) {
+#pragma unroll
+        for (int r = 0; r < KPL; ++r)
+            if (present[r]) {
+                a.Z[t * k + g * KPL + r] = x[r];
+                tr_new = fma(ck[r], x[r], tr_new);
+            }
+    }
+    tr_new = group8_sum(tr_new);
+
+    if (!fused_sample_statistics<KPL>(x, present, valid, k, 0.0, tr_new, wsum, a.cta_part,
+                                      &st->tickets[1]))
+        return;
+    fused_final_sum<KPL>(a.cta_part, fin);
+    // fin[i * KP + j] = (Z'Z)[i][j]; fin[KP * KP + 1] = sum_i a_i (C K Z)[i][i]
+    if (warp == 0) {
+        double t2 = 0.0;
+        for (int idx = lane; idx < k * k; idx += 32) {
+            const int i = idx / k, j = idx % k;
+            t2 += b.alpha[i] * b.alpha[j] * fin[i * KP + j] * b.CKCt[j * k + i];
+        }
+        t2 = warp_sum(t2);
+        if (lane == 0) {
+            // cost after the weights update (archetypal_analysis.py:645-652), stopping rule
+            const double cost = 0.5 * (st->trace_data - 2.0 * fin[KP * KP + 1] + t2) / (double)T;
+            finish_sub_step(st, b.cost_deltas, cost, 3, 1);
+            if (!st->done) st->old_cost = st->cost;    // start of the next iteration
+            st->tickets[1] = 0u;
+        }
+    }
+    for (int idx = threadIdx.x; idx < k * k; idx += blockDim.x)
+        b.ZtZ[idx] = fin[(idx / k) * KP + idx % k];
+}
+
+static size_t aa_fused_smem_bytes(int kp)
+{
+    const int nst = kp * kp + 2;
+    return ((kp > 8 ? (size_t)kp * kp : 0) + (size_t)kFusedWarps * nst + (size_t)nst * 4) * sizeof(double);
+}
+
+static int aa_row_threads(int T)
+{
+    if (T <= 2048) return 256;
+    if (T <= 8192) return 512;
+    return 1024;
+}
+
+// ---------------------------------------------------------------------- workspace layout
+struct AaWorkspace {
+    double* stream;
+    size_t stream_bytes;
+    double* gram;
+    size_t gram_bytes;
+    double* fin_part;     // [ceil(T / 32)][3 * KP * KP]
+    double* cta_part;     // [blocks][KP * KP + 2]
+    size_t total;
+};
+
+static AaWorkspace carve_aa(void* base, int T, int d, int k)
+{
+    AaWorkspace w;
+    const size_t s1 = cdr_reduce_samples_workspace_bytes(T, d, k);
+    const size_t s2 = cdr_reduce_features_workspace_bytes(T, d, k);
+    w.stream_bytes = align256((s1 > s2 ? s1 : s2) + 8);
+    w.gram_bytes = align256(cdr_small_gram_workspace_bytes());
+    const int kp = (k <= 8) ? 8 : 16;
+    int spw = 1, blocks = 1;
+    fused_grid(T, &spw, &blocks);
+    const size_t fp = align256((size_t)((T + kFinTB - 1) / kFinTB) * 3 * kp * kp * sizeof(double));
+    const size_t cp = align256((size_t)blocks * (kp * kp + 2) * sizeof(double));
+    unsigned char* p = static_cast<unsigned char*>(base);
+    w.stream = reinterpret_cast<double*>(p);
+    w.gram = reinterpret_cast<double*>(p + w.stream_bytes);
+    w.fin_part = reinterpret_cast<double*>(p + w.stream_bytes + w.gram_bytes);
+    w.cta_part = reinterpret_cast<double*>(p + w.stream_bytes + w.gram_bytes + fp);
+    w.total = w.stream_bytes + w.gram_bytes + fp + cp;
+    return w;
+}
+
+static bool aa_fused_shape(int T, int d, int k, int dict_max_iterations, int* nstrips)
+{
+    if (k > kFusedMaxK || dict_max_iterations != 1 || T > kAaRowMaxT) return false;
+    const char* e = getenv("CDR_DISABLE_FUSED");
+    if (e != nullptr && e[0] == '1') return false;
+    int out[12];
+    tma_stream_plan(T, d, k, 0, out);
+    if (!out[0] || !out[5]) return false;              // both passes on the strip kernels
+    int TC;
+    return features_strip_geometry(T, d, k, &TC, nstrips);
+}
+
+static int check_aa(const cdr_aa_problem* p)
+{
+    CDR_CHECK_ARG(p != nullptr && p->X != nullptr && p->Z != nullptr && p->tmp_kd != nullptr);
+    const cdr_aa_buffers& b = p->buf;
+    CDR_CHECK_ARG(b.k >= 1 && b.T >= 1 && p->T == b.T && p->d >= 1 && b.ldt >= b.T);
+    CDR_CHECK_ARG(b.C && b.G && b.D && b.CK && b.DK && b.KZt && b.alpha && b.ZtZ && b.CKCt &&
+                  b.CKZ && b.G01 && b.G11 && b.row_scratch && b.state);
+    if (b.k > CDR_MAX_COMPONENTS || b.T > kAaRowMaxT) return CDR_ERR_UNSUPPORTED;
+    if (p->dictionary_params.max_iterations < 1 || p->dictionary_params.max_iterations > 8)
+        return CDR_ERR_UNSUPPORTED;                    // longer inner loops need host control
+    if (p->workspace == nullptr || p->workspace_bytes < cdr_aa_workspace_bytes(p->T, p->d, b.k))
+        return CDR_ERR_WORKSPACE;
+    return 0;
+}
+
+// out (k x ldt) = (L X) X' for a k x T matrix L (row stride ldt)
+static int aa_apply_left(const cdr_aa_problem* p, const AaWorkspace& w, const double* L, double* out,
+                         cudaStream_t s)
+{
+    const cdr_aa_buffers& b = p->buf;
+    CDR_TRY(cdr_reduce_samples(L, b.ldt, 1, p->X, p->ldx, p->T, p->d, b.k, nullptr, p->tmp_kd,
+                               p->ldx, w.stream, w.stream_bytes, b.state, s));
+    return cdr_reduce_features(p->tmp_kd, p->ldx, p->X, p->ldx, p->T, p->d, b.k, out, b.ldt,
+                               w.stream, w.stream_bytes, b.state, s);
+}
+
+// KZt = (X (X' Z))'
+static int aa_apply_right(const cdr_aa_problem* p, const AaWorkspace& w, cudaStream_t s)
+{
+    const cdr_aa_buffers& b = p->buf;
+    CDR_TRY(cdr_reduce_samples(p->Z, 1, b.k, p->X, p->ldx, p->T, p->d, b.k, nullptr, p->tmp_kd,
+                               p->ldx, w.stream, w.stream_bytes, b.state, s));
+    return cdr_reduce_features(p->tmp_kd, p->ldx, p->X, p->ldx, p->T, p->d, b.k, b.KZt, b.ldt,
+                               w.stream, w.stream_bytes, b.state, s);
+}
+
+static cdr_small_gram_desc kt_desc(const cdr_aa_buffers& b, const double* A, const double* B, double* out)
+{
+    return gram_desc(A, b.ldt, 1, b.k, B, b.ldt, 1, b.k, b.T, out, 0);
+}
+
+}  // namespace cdr
+
+using namespace cdr;
+
+extern "C" size_t cdr_aa_workspace_bytes(int T, int d, int k)
+{
+    if (T < 1 || d < 1 || k < 1 || k > CDR_MAX_COMPONENTS) return 0;
+    return carve_aa(nullptr, T, d, k).total;
+}
+
+extern "C" int cdr_aa_fused_applicable(int T, int d, int k, int dictionary_max_iterations)
+{
+    int nstrips;
+    return aa_fused_shape(T, d, k, dictionary_max_iterations, &nstrips) ? 1 : 0;
+}
+
+extern "C" int cdr_aa_prepare_enqueue(const cdr_aa_problem* p, cdr_stream_t stream)
+{
+    CDR_TRY(check_aa(p));
+    cudaStream_t s = (cudaStream_t)stream;
+    const cdr_aa_buffers& b = p->buf;
+    const int k = b.k;
+    const AaWorkspace w = carve_aa(p->workspace, p->T, p->d, k);
+    // archetypal_analysis.py:541-556
+    CDR_TRY(aa_apply_left(p, w, b.C, b.CK, s));
+    CDR_TRY(aa_apply_right(p, w, s));
+    cdr_small_gram_desc ds[3];
+    ds[0] = gram_desc(p->Z, 1, k, k, p->Z, 1, k, k, p->T, b.ZtZ, 0);
+    ds[1] = kt_desc(b, b.CK, b.C, b.CKCt);
+    ds[2] = kt_desc(b, b.C, b.KZt, b.CKZ);
+    CDR_TRY(cdr_small_gram(ds, 3, w.gram, w.gram_bytes, b.state, s));
+    CDR_TRY(cdr_aa_cost_check(&b, 0, 0, s));
+    // spg() starts from project(x0) (spg.py:146-148).  A custom start may only be feasible to
+    // np.isclose accuracy, so C K is rebuilt once for the projected iterate; later iterates
+    // are feasible by construction.
+    CDR_TRY(cdr_simplex_project_rows(b.C, b.C, k, b.T, b.ldt, b.ldt, b.state, s));
+    CDR_TRY(aa_apply_left(p, w, b.C, b.CK, s));
+    ds[0] = kt_desc(b, b.CK, b.C, b.CKCt);
+    CDR_TRY(cdr_small_gram(ds, 1, w.gram, w.gram_bytes, b.state, s));
+    return cdr_loop_begin(b.state, s);
+}
+
+extern "C" int cdr_aa_iterate_enqueue(const cdr_aa_problem* p, cdr_stream_t stream)
+{
+    CDR_TRY(check_aa(p));
+    cudaStream_t s = (cudaStream_t)stream;
+    const cdr_aa_buffers& b = p->buf;
+    const int k = b.k, T = p->T, d = p->d;
+    const AaWorkspace w = carve_aa(p->workspace, T, d, k);
+    const cdr_spg_params& dp = p->dictionary_params;
+    if (dp.memory < 1 || dp.memory > CDR_MAX_MEMORY || p->weights_params.memory < 1 ||
+        p->weights_params.memory > CDR_MAX_MEMORY)
+        return CDR_ERR_UNSUPPORTED;
+    int nstrips = 0;
+
+    if (!aa_fused_shape(T, d, k, dp.max_iterations, &nstrips)) {
+        // general sequence (archetypal_analysis.py:586-663 with the pieces of aa_steps.cu)
+        CDR_TRY(cdr_loop_begin(b.state, s));
+        CDR_TRY(cdr_aa_spg_begin(&b, &dp, s));
+        for (int n = 0; n < dp.max_iterations; ++n) {
+            CDR_TRY(cdr_aa_spg_direction(&b, &dp, s));
+            CDR_TRY(aa_apply_left(p, w, b.D, b.DK, s));
+            cdr_small_gram_desc dg[2] = {kt_desc(b, b.CK, b.D, b.G01), kt_desc(b, b.DK, b.D, b.G11)};
+            CDR_TRY(cdr_small_gram(dg, 2, w.gram, w.gram_bytes, b.state, s));
+            CDR_TRY(cdr_aa_spg_linesearch(&b, &dp, s));
+            if (n + 1 < dp.max_iterations) CDR_TRY(cdr_aa_spg_update(&b, &dp, 1, s));
+        }
+        cdr_small_gram_desc d1[2] = {kt_desc(b, b.CK, b.C, b.CKCt), kt_desc(b, b.C, b.KZt, b.CKZ)};
+        CDR_TRY(cdr_small_gram(d1, 2, w.gram, w.gram_bytes, b.state, s));
+        CDR_TRY(cdr_aa_cost_check(&b, 2, 0, s));
+        CDR_TRY(cdr_quad_simplex_spg_batched(b.CKCt, b.alpha, b.CK, 1, b.ldt, p->Z, T, k,
+                                             &p->weights_params, nullptr, nullptr, b.state, s));
+        CDR_TRY(aa_apply_right(p, w, s));
+        cdr_small_gram_desc d2[2] = {gram_desc(p->Z, 1, k, k, p->Z, 1, k, k, T, b.ZtZ, 0),
+                                     kt_desc(b, b.C, b.KZt, b.CKZ)};
+        CDR_TRY(cdr_small_gram(d2, 2, w.gram, w.gram_bytes, b.state, s));
+        return cdr_aa_cost_check(&b, 3, 1, s);
+    }
+
+    // 1. head: projection, gradient, first step length, direction
+    {
+        const size_t smem = (64 + CDR_MAX_COMPONENTS + (size_t)T) * sizeof(double);
+        CDR_TRY(ensure_dyn_smem<aa_head_kernel>(smem));
+        aa_head_kernel<<<k, aa_row_threads(T), smem, s>>>(b, dp);
+        CDR_RETURN_IF_LAUNCH_FAILED();
+    }
+    // 2. D X    3. (D X) X' as per-strip partials
+    CDR_TRY(cdr_reduce_samples(b.D, b.ldt, 1, p->X, p->ldx, T, d, k, nullptr, p->tmp_kd, p->ldx,
+                               w.stream, w.stream_bytes, b.state, s));
+    {
+        const int rc = run_reduce_features_tma(p->tmp_kd, p->ldx, p->X, p->ldx, T, d, k, nullptr, 0,
+                                               w.stream, w.stream_bytes, b.state, s, nullptr);
+        if (rc != 0) return rc == CDR_TMA_NOT_APPLICABLE ? CDR_ERR_UNSUPPORTED : rc;
+    }
+    // 4. D K, the k x k products, line search, cost check after the dictionary update
+    {
+        const int blocks = (T + kFinTB - 1) / kFinTB;
+        if (k <= 8)
+            aa_finalize_ls_kernel<1><<<blocks, kFinThreads, 0, s>>>(b, dp, w.stream, nstrips, w.fin_part);
+        else
+            aa_finalize_ls_kernel<2><<<blocks, kFinThreads, 0, s>>>(b, dp, w.stream, nstrips, w.fin_part);
+        CDR_RETURN_IF_LAUNCH_FAILED();
+    }
+    // 5. per-sample QPs with the update of C, C K and the statistics
+    {
+        AaWeightsArgs a;
+        a.b = b;
+        a.Z = p->Z;
+        a.cta_part = w.cta_part;
+        a.p = p->weights_params;
+        int blocks;
+        fused_grid(T, &a.spw, &blocks);
+        if (k <= 8) {
+            const size_t smem = aa_fused_smem_bytes(8);
+            CDR_TRY(ensure_dyn_smem<aa_weights_fused_kernel<1>>(smem));
+            aa_weights_fused_kernel<1><<<blocks, kFusedThreads, smem, s>>>(a);
+        } else {
+            const size_t smem = aa_fused_smem_bytes(16);
+            CDR_TRY(ensure_dyn_smem<aa_weights_fused_kernel<2>>(smem));
+            aa_weights_fused_kernel<2><<<blocks, kFusedThreads, smem, s>>>(a);
+        }
+        CDR_RETURN_IF_LAUNCH_FAILED();
+    }
+    // 6.-8. (K Z)' for the next dictionary step
+    return aa_apply_right(p, w, s);
+}

@@ -311,11 +311,16 @@ __device__ __forceinline__ void consumer_barrier()
     asm volatile("bar.sync 1, %0;\n" ::"n"(kConsumerWarps * 32) : "memory");
 }
 
+// Optional by-product (the fused GPNH iteration, iterate.cu): the k x k Gram matrix M M' of the
+// operand itself.  The B fragments of a strip serve as both DMMA operands (a fragment value
+// M[lc][f(lr)] is at once A[lc][lr] and B[lr][lc]); the per-strip results go to
+// gram.part[strip][KP * KP] and the last CTA to finish sums them in strip order into gram.out.
+
 template <int KT, int MAXUQ>
 __global__ void __launch_bounds__(kThreads, 1)
 reduce_features_strip_kernel(const double* __restrict__ M, long ldm, const double* __restrict__ X,
                              long ldx, int T, int dpad, int k, int TC, int nstrips, int stages,
-                             double* __restrict__ part, const cdr_flags* flags)
+                             double* __restrict__ part, const cdr_flags* flags, StripGram gram)
 {
     if (is_done(flags)) return;
     constexpr int KP = 8 * KT;
@@ -382,6 +387,44 @@ reduce_features_strip_kernel(const double* __restrict__ M, long ldm, const doubl
                 }
         }
 
+        if (gram.part != nullptr) {
+            // M M' over the features of this strip: warps with mt == 0 cover the four
+            // feature quarters, which are then combined in fixed order
+            consumer_barrier();          // `red` may still be read by the previous strip's last tile
+            if (mt == 0) {
+                double wacc[KT][KT][2];
+#pragma unroll
+                for (int na = 0; na < KT; ++na)
+#pragma unroll
+                    for (int nb = 0; nb < KT; ++nb) wacc[na][nb][0] = wacc[na][nb][1] = 0.0;
+#pragma unroll
+                for (int uq = 0; uq < MAXUQ; ++uq)
+#pragma unroll
+                    for (int p = 0; p < 2; ++p)
+#pragma unroll
+                        for (int na = 0; na < KT; ++na)
+#pragma unroll
+                            for (int nb = 0; nb < KT; ++nb) {
+                                dmma884(wacc[na][nb][0], wacc[na][nb][1], breg[uq][p][na].x,
+                                        breg[uq][p][nb].x);
+                                dmma884(wacc[na][nb][0], wacc[na][nb][1], breg[uq][p][na].y,
+                                        breg[uq][p][nb].y);
+                            }
+#pragma unroll
+                for (int na = 0; na < KT; ++na)
+#pragma unroll
+                    for (int nb = 0; nb < KT; ++nb)
+                        *reinterpret_cast<double2*>(red + fq * KP * KP + (na * 8 + lc) * KP +
+                                                    nb * 8 + 2 * lr) =
+                            make_double2(wacc[na][nb][0], wacc[na][nb][1]);
+            }
+            consumer_barrier();
+            for (int e = threadIdx.x; e < KP * KP; e += kConsumerWarps * 32)
+                gram.part[(long)strip * KP * KP + e] =
+                    ((red[e] + red[KP * KP + e]) + red[2 * KP * KP + e]) + red[3 * KP * KP + e];
+            consumer_barrier();
+        }
+
         for (int rt = 0; rt < ntiles; ++rt, ++it) {
             const int s = it % stages;
             const uint32_t ph = (uint32_t)(it / stages) & 1u;
@@ -434,6 +477,34 @@ reduce_features_strip_kernel(const double* __restrict__ M, long ldm, const doubl
                     *reinterpret_cast<double2*>(dst + nt * 8) = make_double2(s0, s1);
                 }
             }
+        }
+    }
+
+    if (gram.part != nullptr) {
+        // the last CTA to get here sums the per-strip Gram matrices in strip order
+        int* last = reinterpret_cast<int*>(red + 4 * KP * KP);
+        __threadfence();
+        consumer_barrier();
+        if (threadIdx.x == 0) *last = (atomicAdd(gram.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+        consumer_barrier();
+        if (*last) {
+            __threadfence();
+            constexpr int E = KP * KP;                       // 64 or 256
+            constexpr int NSUB = (kConsumerWarps * 32) / E;  // 4 or 1
+            const int e = (int)threadIdx.x % E, sub = (int)threadIdx.x / E;
+            double sacc = 0.0;
+            for (int sidx = sub; sidx < nstrips; sidx += NSUB)
+                sacc += __ldcg(gram.part + (long)sidx * E + e);
+            red[sub * E + e] = sacc;
+            consumer_barrier();
+            if (sub == 0) {
+                double tot = red[e];
+#pragma unroll
+                for (int q = 1; q < NSUB; ++q) tot += red[q * E + e];
+                const int i = e / KP, j = e % KP;
+                if (i < k && j < k) gram.out[i * k + j] = tot;
+            }
+            if (threadIdx.x == 0) *gram.ticket = 0u;
         }
     }
 }
@@ -681,7 +752,7 @@ template <int KT>
 static int launch_features_strip(const double* M, long ldm, const double* X, long ldx, int T,
                                  int dpad, int k, int TC, int nstrips, double* out, long ldo,
                                  void* workspace, size_t workspace_bytes, const cdr_flags* flags,
-                                 cudaStream_t stream)
+                                 cudaStream_t stream, const StripGram& gram)
 {
     constexpr int KP = 8 * KT;
     constexpr int MAXUQ = kFsTcMax / 16 / 4;
@@ -696,8 +767,9 @@ static int launch_features_strip(const double* M, long ldm, const double* X, lon
     if (rc) return rc;
     const int grid = nstrips < sm_count() ? nstrips : sm_count();
     reduce_features_strip_kernel<KT, MAXUQ><<<grid, kThreads, smem, stream>>>(
-        M, ldm, X, ldx, T, dpad, k, TC, nstrips, stages, (double*)workspace, flags);
+        M, ldm, X, ldx, T, dpad, k, TC, nstrips, stages, (double*)workspace, flags, gram);
     CDR_RETURN_IF_LAUNCH_FAILED();
+    if (out == nullptr) return 0;          // the caller consumes the per-strip partials itself
     const long nitems = (long)T * (KP / 2);
     reduce_features_strip_finalize_kernel<KT><<<(int)((nitems + 31) / 32), 256, 0, stream>>>(
         (const double*)workspace, T, nstrips, k, out, ldo, flags);
@@ -745,16 +817,26 @@ void tma_stream_plan(int T, int d, int k, int with_epilogue, int* out)
 
 int run_reduce_features_tma(const double* M, long ldm, const double* X, long ldx, int T, int d,
                             int k, double* out, long ldo, void* workspace, size_t workspace_bytes,
-                            const cdr_flags* flags, cudaStream_t stream)
+                            const cdr_flags* flags, cudaStream_t stream, const StripGram* gram)
 {
     int TC, nstrips;
     if (!features_strip_ok(M, ldm, X, ldx, T, d, k, &TC, &nstrips)) return CDR_TMA_NOT_APPLICABLE;
     const int dpad = (d + 31) / 32 * 32;
+    StripGram g = {nullptr, nullptr, nullptr};
+    if (gram != nullptr) g = *gram;
     if (k <= 8)
         return launch_features_strip<1>(M, ldm, X, ldx, T, dpad, k, TC, nstrips, out, ldo, workspace,
-                                        workspace_bytes, flags, stream);
+                                        workspace_bytes, flags, stream, g);
     return launch_features_strip<2>(M, ldm, X, ldx, T, dpad, k, TC, nstrips, out, ldo, workspace,
-                                    workspace_bytes, flags, stream);
+                                    workspace_bytes, flags, stream, g);
+}
+
+// Strip geometry of the reduce over features (for callers that consume the per-strip
+// partials part[strip][t][KP] themselves): false when the strip kernel does not apply.
+bool features_strip_geometry(int T, int d, int k, int* TC, int* nstrips)
+{
+    if (tma_disabled()) return false;
+    return features_strip_plan(T, (d + 31) / 32 * 32, k, TC, nstrips);
 }
 
 }  // namespace cdr

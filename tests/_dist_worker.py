@@ -174,6 +174,12 @@ def run_gloo(out):
 
     rows = comm.allgather_rows(Zl)
     assert np.array_equal(rows, Z0)
+    # ranks seeded differently (random_state=None in the estimators): after the sync every
+    # rank draws what rank 0 would have drawn
+    rng = np.random.RandomState(100 + rank)
+    comm.sync_random_state(rng)
+    draws = comm.allgather_objects(rng.uniform(size=4).tolist())
+    assert draws[0] == draws[1] == np.random.RandomState(100).uniform(size=4).tolist()
     replicated_restarts_check(comm)
     row_helpers_check(comm, X)
     mx = torch.tensor([float(rank)], dtype=torch.float64)

@@ -91,6 +91,25 @@ def test_solver_and_helper_signatures():
     assert [n for n, _ in params(sp.simplex_project_vector)] == ['x']
 
 
+def test_gap_statistic_signature_is_the_reference_one():
+    # kmeans.py:81-82; the drivers call gap_statistic(X, model.inertia_, n_components=k,
+    # n_trials=..., reference=..., n_jobs=..., random_state=...) (bin/run_jra55_kmeans.py:128)
+    from convex_dim_red import kmeans as km
+    assert params(cdr.gap_statistic) == [
+        ('X', E), ('Wk', E), ('n_components', E), ('n_trials', 100), ('reference', 'uniform'),
+        ('n_jobs', 1), ('random_state', None)]
+    assert params(km._calculate_uniform_reference_wk) == [
+        ('X', E), ('n_clusters', E), ('n_init', 10), ('n_jobs', None), ('random_state', None)]
+    assert params(km._calculate_pca_reference_wk) == [
+        ('X', E), ('n_clusters', E), ('n_init', 10), ('n_components', 100), ('n_iter', 10),
+        ('n_jobs', None), ('random_state', None)]
+    # the driver's call pattern binds
+    inspect.signature(cdr.gap_statistic).bind(np.zeros((4, 3)), 1.5, n_components=2, n_trials=3,
+                                              reference='pca', n_jobs=2, random_state=0)
+    with pytest.raises(ValueError, match='unrecognized reference distribution'):
+        km._calculate_reference_wk(np.zeros((4, 3)), 2, reference='box')
+
+
 def test_private_helpers_used_by_the_reference_tests():
     # tests/test_archetypal_analysis.py:14-18, tests/test_gpnh_convex_coding.py:13-15
     assert params(aa._kernel_aa_cost) == [('K', E), ('weights', E), ('dictionary', E), ('alpha', E)]

@@ -503,3 +503,39 @@ def test_tiny_and_degenerate_shapes_match_oracle(T, d, k):
         rl, rc, ri, rn = orc.kmeans_lloyd(X, X[:k].copy())
         assert np.array_equal(labels, rl) and n_iter == rn
         close(centres, rc, rtol=1e-10, atol=1e-12)
+
+
+def test_gap_statistic_follows_the_reference_protocol():
+    """gap_statistic (kmeans.py:81-108) against the reference's own code path with
+    scikit-learn's KMeans in place (the reference passes the removed `n_jobs` to KMeans, so its
+    body is restated here with that argument dropped): same per-trial seeds, same reference
+    data, same k-means++ seeding and Lloyd iterations -> the same dispersions."""
+    from sklearn.cluster import KMeans as SkKMeans
+    from sklearn.utils import check_random_state
+    from convex_dim_red import kmeans as km
+    rs = np.random.RandomState(3)
+    centres = rs.standard_normal((3, 20)) * 4
+    X = centres[rs.randint(3, size=120)] + rs.standard_normal((120, 20))
+    k, n_trials = 3, 3
+    model = km.KMeans(n_clusters=k, init='k-means++', n_init=2, random_state=0).fit(X)
+    gap, sk = cdr.gap_statistic(X, model.inertia_, n_components=k, n_trials=n_trials,
+                                reference='uniform', n_jobs=1, random_state=5)
+
+    rng = check_random_state(5)
+    seeds = []
+    for _ in range(n_trials):
+        while True:
+            seed = rng.randint(np.iinfo(np.int32).max)
+            if seed not in seeds:
+                seeds.append(seed)
+                break
+    wk = []
+    for seed in seeds:
+        r = check_random_state(seed)
+        lo = np.broadcast_to(X.min(axis=0), X.shape)
+        hi = np.broadcast_to(X.max(axis=0), X.shape)
+        data = (hi - lo) * r.uniform(size=X.shape) + lo
+        wk.append(SkKMeans(n_clusters=k, n_init=10, random_state=r).fit(data).inertia_)
+    ln = np.log(np.array(wk))
+    np.testing.assert_allclose(gap, ln.mean() - np.log(model.inertia_), rtol=1e-9)
+    np.testing.assert_allclose(sk, np.std(ln) * np.sqrt(1 + 1.0 / n_trials), rtol=1e-6, atol=1e-12)

@@ -103,6 +103,11 @@ unsigned long long cdr_launch_count(void); /* kernels launched by this library s
 /* host-only: kernel choice and tile geometry of the two streaming passes for a shape
  * (12 ints, see stream_gemm.cu); lets the dispatch logic be tested without a GPU */
 int cdr_debug_stream_plan(int T, int d, int k, int with_epilogue, int* out);
+/* fp64 tensor-pipe (DMMA.8x8x4) throughput probe: `blocks` CTAs x 8 warps x 8 independent
+ * chains x `iters` MMAs on registers; out: blocks * 256 doubles.  The caller times the launch;
+ * flops = 2 * 256 * 8 * iters * 8 * blocks.  The result is the roofline denominator of the
+ * tensor-bound shapes (Gram, k = 64), which MEASURED_PEAKS.json does not carry. */
+int cdr_debug_dmma_probe(double* out, int blocks, int iters, cdr_stream_t stream);
 
 /* ------------------------------------------------------------------ simplex
  * Euclidean projection of each row / column of A onto the probability simplex.
@@ -308,6 +313,7 @@ int cdr_center_columns(double* X, long ldx, int T, int d, const double* mean, do
 #define CDR_PEER_HEADER_BYTES (1u << 20)
 #define CDR_PEER_MAX_CTAS 256    /* grid limit of the collective kernels */
 #define CDR_PEER_MAX_STRIPS 2048 /* strips of the fused reduce-over-samples kernel */
+#define CDR_PEER_SMALL_MAX 800   /* doubles of a one-shot exchange between kernel tails */
 
 typedef struct cdr_peer_group {
     int world;
@@ -364,10 +370,10 @@ int cdr_reduce_samples_allreduce(const cdr_peer_group* group, const double* Lp, 
  * zero).  Protocol:   prepare_enqueue once, then iterate_enqueue until state->done.
  */
 typedef struct cdr_gpnh_problem {
-    const double* X;      /* T x d data, leading dimension ldx */
+    const double* X;      /* T x d data (this rank's rows), leading dimension ldx */
     long ldx;
     int T, d, k;
-    int T_total;          /* = T (single GPU) */
+    int T_total;          /* = T on a single GPU; all ranks' rows in a sample-sharded fit */
     double lambda_W;
     double* Z;            /* T x k weights, dense, updated in place */
     double* WT;           /* k x ldx: the dictionary transposed (gpnh_convex_coding.py:226), updated in place */
@@ -383,6 +389,13 @@ typedef struct cdr_gpnh_problem {
     cdr_spg_params weights_params;
     void* workspace;      /* cdr_gpnh_workspace_bytes(T, d, k) */
     size_t workspace_bytes;
+    /* sample-sharded fit over peer memory (NULL / world 1: single GPU): WT must live in the
+     * symmetric region (same offset on every rank), with an inbox slot of k * ldx doubles;
+     * T_min = the smallest local T of any rank.  Only cdr_gpnh_iterate_enqueue on the
+     * three-kernel path is offered; the statistics of the first iteration (Z'Z summed over
+     * ranks, cost, old_cost, P) are the caller's to form. */
+    const cdr_peer_group* peers;
+    int T_min;
 } cdr_gpnh_problem;
 
 size_t cdr_gpnh_workspace_bytes(int T, int d, int k);
@@ -403,16 +416,26 @@ int cdr_gpnh_fused_applicable(int T, int d, int k); /* host-only: 1 = three-kern
  * factor update), dictionary SPG with 1 <= max_iterations <= 8 inner iterations (longer inner
  * loops need the host to look at the state between bursts: use the cdr_aa_spg_* pieces). */
 typedef struct cdr_aa_problem {
-    const double* X;      /* T x d data, leading dimension ldx */
+    const double* X;      /* T x d data (this rank's rows), leading dimension ldx */
     long ldx;
     int T, d;
-    cdr_aa_buffers buf;   /* C, G, D, CK, DK, KZt (k x ldt), alpha, k x k statistics, state */
+    cdr_aa_buffers buf;   /* C, G, D, CK, DK, KZt (k x ldt), alpha, k x k statistics, state;
+                             buf.T = all samples (= T on a single GPU) */
     double* Z;            /* T x k weights, dense, updated in place */
     double* tmp_kd;       /* k x ldx scratch: D X, Z'X */
     cdr_spg_params dictionary_params; /* defaults spg.py:46-51 */
     cdr_spg_params weights_params;    /* defaults spg.py:287-291 */
     void* workspace;      /* cdr_aa_workspace_bytes(T, d, k) */
     size_t workspace_bytes;
+    /* sample-sharded fit over peer memory (NULL / world 1: single GPU, row0 = 0): this rank
+     * owns samples row0 .. row0 + T; the k x buf.T matrices are replicated; DK, KZt and tmp_kd
+     * must live in the symmetric region (same offsets on every rank) with an inbox slot of
+     * k * ldx doubles; T_min = the smallest local T of any rank.  Only cdr_aa_iterate_enqueue
+     * on the eight-kernel path is offered; the products of the first iteration are the
+     * caller's to form. */
+    int row0;
+    int T_min;
+    const cdr_peer_group* peers;
 } cdr_aa_problem;
 
 size_t cdr_aa_workspace_bytes(int T, int d, int k);

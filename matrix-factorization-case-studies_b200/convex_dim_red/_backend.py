@@ -90,7 +90,8 @@ class GpnhProblem(ctypes.Structure):
                 ('WtW', ctypes.c_void_p), ('REG', ctypes.c_void_p), ('P', ctypes.c_void_p),
                 ('state', ctypes.c_void_p), ('cost_deltas', ctypes.c_void_p),
                 ('weights_params', SpgParams), ('workspace', ctypes.c_void_p),
-                ('workspace_bytes', ctypes.c_size_t)]
+                ('workspace_bytes', ctypes.c_size_t),
+                ('peers', ctypes.c_void_p), ('T_min', ctypes.c_int)]
 
 
 class AaProblem(ctypes.Structure):
@@ -100,7 +101,8 @@ class AaProblem(ctypes.Structure):
                 ('T', ctypes.c_int), ('d', ctypes.c_int), ('buf', AaBuffers),
                 ('Z', ctypes.c_void_p), ('tmp_kd', ctypes.c_void_p),
                 ('dictionary_params', SpgParams), ('weights_params', SpgParams),
-                ('workspace', ctypes.c_void_p), ('workspace_bytes', ctypes.c_size_t)]
+                ('workspace', ctypes.c_void_p), ('workspace_bytes', ctypes.c_size_t),
+                ('row0', ctypes.c_int), ('T_min', ctypes.c_int), ('peers', ctypes.c_void_p)]
 
 
 MAX_PEERS = 8
@@ -123,6 +125,7 @@ SIGNATURES = {
     'cdr_device_check': (_i, []),
     'cdr_launch_count': (ctypes.c_ulonglong, []),
     'cdr_debug_stream_plan': (_i, [_i, _i, _i, _i, ctypes.POINTER(ctypes.c_int)]),
+    'cdr_debug_dmma_probe': (_i, [_vp, _i, _i, _vp]),
     'cdr_simplex_project_rows': (_i, [_vp, _vp, _i, _i, _l, _l, _vp, _vp]),
     'cdr_simplex_project_columns': (_i, [_vp, _vp, _i, _i, _l, _l, _vp, _vp]),
     'cdr_quad_simplex_spg_batched': (_i, [_vp, _vp, _vp, _l, _l, _vp, _i, _i,
@@ -451,6 +454,33 @@ def gram_slabs(X, T, d):
     check(lib.cdr_gram(ptr(X), X.stride(0), T, d, ptr(K), K.stride(0), ptr(ws),
                        ws.numel() * 8, stream_ptr()), 'cdr_gram')
     return K
+
+
+_DMMA_PEAK = [None]
+
+
+def dmma_peak_tflops():
+    """Measured fp64 tensor-pipe peak of this GPU (DMMA.8x8x4 on registers, best of 5 launches,
+    CUDA events): the roofline denominator of the tensor-bound shapes."""
+    if _DMMA_PEAK[0] is None:
+        torch = require_cuda()
+        lib = library()
+        blocks, iters = 148 * 4, 20000
+        out = torch.empty(blocks * 256, dtype=torch.float64, device='cuda')
+        best = None
+        for _ in range(6):
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            check(lib.cdr_debug_dmma_probe(ptr(out), blocks, iters, stream_ptr()),
+                  'cdr_debug_dmma_probe')
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None or ms < best else best
+        flops = 2.0 * 256 * 8 * iters * 8 * blocks
+        _DMMA_PEAK[0] = flops / (best * 1e-3) / 1e12
+    return _DMMA_PEAK[0]
 
 
 _TRACE_T0 = [None]

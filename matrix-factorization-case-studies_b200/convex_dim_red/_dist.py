@@ -43,7 +43,7 @@ class Comm:
         self.peer = None          # _peer.PeerGroup once setup_peer() has run ...
         self.peer_on = False      # ... and whether the current fit uses it
 
-    # -- peer-memory collectives (opt-in, CDR_PEER_COLLECTIVES=1) ---------------------------
+    # -- peer-memory collectives (default for NCCL groups; CDR_PEER_COLLECTIVES=0 disables) ---
     def setup_peer(self, shapes, inbox_shape):
         """Prepare the symmetric region for the fp64 tensors ``shapes`` (allocated afterwards,
         in this order, with :meth:`zeros`) and a per-rank inbox slot of ``inbox_shape``.
@@ -51,7 +51,8 @@ class Comm:
         None when peer collectives are off (then :meth:`zeros` gives ordinary tensors and the
         collectives go through ``torch.distributed``)."""
         from . import _peer
-        self.peer_on = self.enabled and _peer.peer_collectives_enabled()
+        self.peer_on = (self.enabled and self.device() == 'cuda' and
+                        _peer.peer_collectives_enabled())
         if not self.peer_on:
             return None
         count = lambda shape: int(np.prod(shape))

@@ -9,9 +9,10 @@ pull it over NVLink directly: the sum over ranks of a k x d partial, fused into 
 of the reduce-over-samples kernel where the strip kernel applies, the sum of the small k x k
 statistics, and the all-gather of k x T_local column blocks.
 
-Opt-in for now: set ``CDR_PEER_COLLECTIVES=1`` (the default path uses NCCL through
-``torch.distributed``).  PyTorch still owns streams; the region itself is ``cudaMalloc``
-memory owned by the library, wrapped zero-copy as tensors.
+On by default for NCCL process groups (validated on 2 and 8 B200s, profiles/r02);
+``CDR_PEER_COLLECTIVES=0`` falls back to NCCL through ``torch.distributed``.  PyTorch still
+owns streams; the region itself is ``cudaMalloc`` memory owned by the library, wrapped
+zero-copy as tensors.
 """
 
 import ctypes
@@ -23,7 +24,7 @@ ALIGN = 512
 
 
 def peer_collectives_enabled():
-    return os.environ.get('CDR_PEER_COLLECTIVES', '0') == '1'
+    return os.environ.get('CDR_PEER_COLLECTIVES', '1') != '0'
 
 
 def round_up(n, m=ALIGN):

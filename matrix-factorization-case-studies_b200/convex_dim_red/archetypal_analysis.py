@@ -160,21 +160,28 @@ class _AaEngine:
             self.G01.data_ptr(), self.G11.data_ptr(), self.row_scratch.data_ptr(),
             self.state.ptr, self.state.cost_deltas.data_ptr(), k, T, ldt, grad_scale, 1.0 / k)
         self._first_dictionary_update = True
-        # single-GPU feature-space fits with a short inner SPG loop and no scale-factor update
-        # run behind the C entry points cdr_aa_prepare_enqueue / cdr_aa_iterate_enqueue
-        # (eight kernels per outer iteration at streaming shapes with one inner iteration)
-        self.c_loop = (mode == 'feature' and not self.comm.enabled and update_weights and
-                       update_dictionary and not (update_scale_factors and delta != 0) and
-                       1 <= self.d_params.max_iterations <= _MAX_UNROLLED_SPG)
+        # feature-space fits with a short inner SPG loop and no scale-factor update run behind
+        # the C entry points cdr_aa_prepare_enqueue / cdr_aa_iterate_enqueue (eight kernels per
+        # outer iteration at streaming shapes with one inner iteration): always on a single
+        # GPU, and for a sample-sharded fit when the peer-memory collectives are on and the
+        # eight-kernel path covers the shape
+        eligible = (mode == 'feature' and update_weights and update_dictionary and
+                    not (update_scale_factors and delta != 0) and
+                    1 <= self.d_params.max_iterations <= _MAX_UNROLLED_SPG)
+        self.c_sharded = (eligible and self.comm.enabled and self.peer is not None and
+                          bool(self.lib.cdr_aa_fused_applicable(
+                              min(self.sizes), self.d, k, self.d_params.max_iterations)))
+        self.c_loop = (eligible and not self.comm.enabled) or self.c_sharded
         if self.c_loop:
-            nbytes = self.lib.cdr_aa_workspace_bytes(T, self.d, k)
+            nbytes = self.lib.cdr_aa_workspace_bytes(self.Tl, self.d, k)
             self.c_ws = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device='cuda')
             self.problem = be.AaProblem(
-                self.X.data_ptr(), self.ldx, T, self.d, self.buf, self.Z.data_ptr(),
+                self.X.data_ptr(), self.ldx, self.Tl, self.d, self.buf, self.Z.data_ptr(),
                 self.tmp_kd.data_ptr(), self.d_params, self.w_params, self.c_ws.data_ptr(),
-                self.c_ws.numel() * 8)
+                self.c_ws.numel() * 8, self.lo, min(self.sizes),
+                ctypes.addressof(self.peer.struct) if self.c_sharded else None)
             self.fused = bool(self.lib.cdr_aa_fused_applicable(
-                T, self.d, k, self.d_params.max_iterations))
+                min(self.sizes), self.d, k, self.d_params.max_iterations))
 
     # -- products with K ----------------------------------------------------
     def _samples_sum(self, L, sLi, sLt, flags):
@@ -240,13 +247,30 @@ class _AaEngine:
         self.comm.allreduce_sum(self.ZtZ)
 
     def initial_cost(self):
-        if self.c_loop:
+        if self.c_loop and not self.c_sharded:
             be.check(self.lib.cdr_aa_prepare_enqueue(ctypes.byref(self.problem),
                                                      be.stream_ptr()), 'cdr_aa_prepare_enqueue')
             self._first_dictionary_update = False
             return
         self.precompute()
         self._cost_check(0, False)
+        if self.c_sharded:
+            # what cdr_aa_prepare_enqueue does next on one GPU: the projection of the start
+            # (spg.py:146-148) and old_cost
+            self._project_start()
+            be.check(self.lib.cdr_loop_begin(self.state.ptr, be.stream_ptr()), 'cdr_loop_begin')
+
+    def _project_start(self):
+        """spg() starts from project(x0) (spg.py:146-148).  A custom start may only be
+        feasible to np.isclose accuracy, so C K is rebuilt for the projected iterate once;
+        later iterates are feasible by construction."""
+        fl = self.state.ptr
+        be.check(self.lib.cdr_simplex_project_rows(
+            self.C.data_ptr(), self.C.data_ptr(), self.k, self.T, self.ldt, self.ldt, fl,
+            be.stream_ptr()), 'cdr_simplex_project_rows')
+        self.apply_left(self.C, self.CK, fl)
+        be.small_gram([self._desc(self.CK, self.C, self.CKCt)], self.ws, fl)
+        self._first_dictionary_update = False
 
     def spg_iteration(self, last):
         """One iteration of spg.py:165-281 on the dictionary."""
@@ -266,15 +290,7 @@ class _AaEngine:
         fl = self.state.ptr
         buf, p = ctypes.byref(self.buf), ctypes.byref(self.d_params)
         if self._first_dictionary_update:
-            # spg() starts from project(x0) (spg.py:146-148).  A custom start may only
-            # be feasible to np.isclose accuracy, so C K is rebuilt for the projected
-            # iterate once; later iterates are feasible by construction.
-            be.check(self.lib.cdr_simplex_project_rows(
-                self.C.data_ptr(), self.C.data_ptr(), self.k, self.T, self.ldt, self.ldt, fl,
-                be.stream_ptr()), 'cdr_simplex_project_rows')
-            self.apply_left(self.C, self.CK, fl)
-            be.small_gram([self._desc(self.CK, self.C, self.CKCt)], self.ws, fl)
-            self._first_dictionary_update = False
+            self._project_start()
         be.check(self.lib.cdr_aa_spg_begin(buf, p, be.stream_ptr()), 'cdr_aa_spg_begin')
         max_it = self.d_params.max_iterations
         if max_it <= _MAX_UNROLLED_SPG:

@@ -98,19 +98,26 @@ class _GpnhEngine:
         self.comm.allreduce_max(t_min)
         self.T_min = -int(t_min.item())      # smallest local T: keeps kernel choices identical
         self.lib = be.library()
-        # single-GPU full iterations run behind the C entry points cdr_gpnh_prepare_enqueue /
-        # cdr_gpnh_iterate_enqueue (three kernels per iteration at streaming shapes, k <= 16)
-        self.c_loop = (not self.comm.enabled) and update_dictionary and update_weights
+        # full iterations run behind the C entry points cdr_gpnh_prepare_enqueue /
+        # cdr_gpnh_iterate_enqueue (three kernels per iteration at streaming shapes, k <= 16):
+        # always on a single GPU, and for a sample-sharded fit when the peer-memory collectives
+        # are on and the three-kernel path covers the shape
+        full = update_dictionary and update_weights
+        self.c_sharded = (full and self.comm.enabled and self.peer is not None and
+                          bool(self.lib.cdr_gpnh_fused_applicable(self.T_min, d, k)))
+        self.c_loop = (full and not self.comm.enabled) or self.c_sharded
         if self.c_loop:
             nbytes = self.lib.cdr_gpnh_workspace_bytes(T, d, k)
             self.c_ws = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device='cuda')
             self.problem = be.GpnhProblem(
-                self.X.data_ptr(), self.ldx, T, d, k, T, self.lambda_W, self.Z.data_ptr(),
-                self.WT.data_ptr(), self.XWt.data_ptr(), self.ldt, self.ZtZ.data_ptr(),
-                self.XWtZ.data_ptr(), self.WtW.data_ptr(), self.REG.data_ptr(),
-                self.P.data_ptr(), self.state.ptr, self.state.cost_deltas.data_ptr(),
-                self.params, self.c_ws.data_ptr(), self.c_ws.numel() * 8)
-            self.fused = bool(self.lib.cdr_gpnh_fused_applicable(T, d, k))
+                self.X.data_ptr(), self.ldx, T, d, k, self.T_total, self.lambda_W,
+                self.Z.data_ptr(), self.WT.data_ptr(), self.XWt.data_ptr(), self.ldt,
+                self.ZtZ.data_ptr(), self.XWtZ.data_ptr(), self.WtW.data_ptr(),
+                self.REG.data_ptr(), self.P.data_ptr(), self.state.ptr,
+                self.state.cost_deltas.data_ptr(), self.params, self.c_ws.data_ptr(),
+                self.c_ws.numel() * 8,
+                ctypes.addressof(self.peer.struct) if self.c_sharded else None, self.T_min)
+            self.fused = bool(self.lib.cdr_gpnh_fused_applicable(self.T_min, d, k))
 
     # -- small products -----------------------------------------------------
     def _desc_ZtZ(self):
@@ -141,7 +148,7 @@ class _GpnhEngine:
     # -- pieces of the loop -------------------------------------------------
     def initial_cost(self):
         """gpnh_convex_coding.py:292-314."""
-        if self.c_loop:
+        if self.c_loop and not self.c_sharded:
             be.check(self.lib.cdr_gpnh_prepare_enqueue(ctypes.byref(self.problem),
                                                        be.stream_ptr()),
                      'cdr_gpnh_prepare_enqueue')
@@ -154,6 +161,12 @@ class _GpnhEngine:
         be.small_gram(descs, self.ws, flags)
         self.comm.allreduce_sum(self.stats[:2])
         self._cost_check(0, False, self.lambda_W != 0)
+        if self.c_sharded:
+            # start of the first iteration, as cdr_gpnh_prepare_enqueue does on one GPU
+            be.check(self.lib.cdr_loop_begin(self.state.ptr, be.stream_ptr()), 'cdr_loop_begin')
+            be.check(self.lib.cdr_gpnh_solve_matrix(
+                self.ZtZ.data_ptr(), self.k, self.T_total, self.d, self.lambda_W,
+                self.P.data_ptr(), None, 0, flags, be.stream_ptr()), 'cdr_gpnh_solve_matrix')
 
     def dictionary_step(self, stage=2, end=False, flags=True):
         """gpnh_convex_coding.py:348-369 (one pass Z'X with the k x k solve folded

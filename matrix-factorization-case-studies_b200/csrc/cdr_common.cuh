@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/cdr_b200.h"
 
@@ -15,12 +17,28 @@
 // Launch-error check used by every C-ABI entry point (no synchronisation:
 // all entry points are asynchronous on the caller's stream).
 // Also counts kernel launches (cdr_launch_count): the macro follows every <<<>>>.
+// CDR_DEBUG_SYNC=1 (debugging aid): synchronise after every launch and report the first
+// failing one with its source line.
 extern unsigned long long cdr_g_kernel_launches;
-#define CDR_RETURN_IF_LAUNCH_FAILED()                         \
-    do {                                                      \
-        cudaError_t e__ = cudaGetLastError();                 \
-        if (e__ != cudaSuccess) return (int)e__;              \
-        ++cdr_g_kernel_launches;                              \
+static inline bool cdr_debug_sync()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("CDR_DEBUG_SYNC");
+        v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+#define CDR_RETURN_IF_LAUNCH_FAILED()                                                       \
+    do {                                                                                    \
+        cudaError_t e__ = cudaGetLastError();                                               \
+        if (e__ == cudaSuccess && cdr_debug_sync()) e__ = cudaDeviceSynchronize();          \
+        if (e__ != cudaSuccess) {                                                           \
+            if (cdr_debug_sync())                                                           \
+                fprintf(stderr, "[cdr] %s:%d: %s\n", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return (int)e__;                                                                \
+        }                                                                                   \
+        ++cdr_g_kernel_launches;                                                            \
     } while (0)
 
 #define CDR_CHECK_ARG(cond)                                   \

@@ -17,6 +17,7 @@
 //
 // All reductions have a fixed order, so results are bit-reproducible run to run.
 #include "fused_weights.cuh"
+#include "peer.cuh"
 #include "small_solve.cuh"
 
 namespace cdr {
@@ -35,6 +36,7 @@ struct GpnhFusedArgs {
     int T, k, d, T_total, spw;
     double lambda_W;
     cdr_spg_params p;
+    cdr_peer_group g;        // world == 1: single GPU
 };
 
 template <int KPL>
@@ -108,7 +110,7 @@ gpnh_weights_fused_kernel(GpnhFusedArgs a)
     tr_old = group8_sum(tr_old);
 
     int n_iter = 0, n_feval = 0;
-    qp_solve<KPL>(As, arow, z0, b, present, a.p, valid, g, x, n_iter, n_feval);
+    qp_solve<KPL>(As, arow, z0, b, present, a.p, has_sample, g, spw, x, n_iter, n_feval);
 
     double tr_new = 0.0;
     if (valid) {
@@ -125,6 +127,8 @@ gpnh_weights_fused_kernel(GpnhFusedArgs a)
                                       &st->tickets[1]))
         return;
     fused_final_sum<KPL>(a.cta_part, fin);
+    // sample-sharded fit: the statistics of all ranks, summed in rank order on every rank
+    if (a.g.world > 1) peer::cta_allreduce_small(a.g, fin, NST);
     // fin[i * KP + j] = (Z'Z)[i][j] of the new weights; fin[KP*KP], fin[KP*KP+1] the traces
     if (warp == 0) {
         double tp = 0.0, tn = 0.0, phi = 0.0;
@@ -219,15 +223,17 @@ static GpnhWorkspace carve_gpnh(void* base, int T, int d, int k)
 
 static bool gpnh_fused_applicable(const cdr_gpnh_problem* p, int* TC, int* nstrips)
 {
+    const bool sharded = p->peers != nullptr && p->peers->world > 1;
+    const int T = sharded ? p->T_min : p->T;       // every rank must take the same decision
     if (p->k > kFusedMaxK) return false;
     const char* e = getenv("CDR_DISABLE_FUSED");
     if (e != nullptr && e[0] == '1') return false;
     if ((p->ldx % 2) != 0 || (((uintptr_t)p->X) & 15) != 0 || (((uintptr_t)p->WT) & 15) != 0)
         return false;
     int out[12];
-    tma_stream_plan(p->T, p->d, p->k, 1, out);
+    tma_stream_plan(T, p->d, p->k, 1, out);
     if (!out[0] || !out[5]) return false;              // both passes on the strip kernels
-    return features_strip_geometry(p->T, p->d, p->k, TC, nstrips);
+    return features_strip_geometry(T, p->d, p->k, TC, nstrips);
 }
 
 static int check_gpnh(const cdr_gpnh_problem* p)
@@ -278,6 +284,8 @@ extern "C" int cdr_gpnh_fused_applicable(int T, int d, int k)
 extern "C" int cdr_gpnh_prepare_enqueue(const cdr_gpnh_problem* p, cdr_stream_t stream)
 {
     CDR_TRY(check_gpnh(p));
+    // sample-sharded fits: the caller forms the initial statistics with its own collectives
+    if (p->peers != nullptr && p->peers->world > 1) return CDR_ERR_UNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
     const GpnhWorkspace w = carve_gpnh(p->workspace, p->T, p->d, p->k);
     // gpnh_convex_coding.py:292-314
@@ -300,11 +308,23 @@ extern "C" int cdr_gpnh_iterate_enqueue(const cdr_gpnh_problem* p, cdr_stream_t 
     const double* reg = p->lambda_W != 0.0 ? p->REG : nullptr;
     int TC = 0, nstrips = 0;
 
-    // W' = P Z'X  (gpnh_convex_coding.py:219-226)
-    CDR_TRY(cdr_reduce_samples(p->Z, 1, k, p->X, p->ldx, T, d, k, p->P, p->WT, p->ldx, w.stream,
-                               w.stream_bytes, p->state, s));
+    const bool sharded = p->peers != nullptr && p->peers->world > 1;
+    const bool fused = gpnh_fused_applicable(p, &TC, &nstrips);
+    if (sharded) {
+        // W' = P sum_r Z_r' X_r: the strip kernel with the sum over ranks in its epilogue
+        // (stream_tma.cu); only the three-kernel path is offered over peer memory
+        if (!fused) return CDR_ERR_UNSUPPORTED;
+        CDR_CHECK_ARG(p->T_min >= 1 && p->T_min <= T);
+        CDR_TRY(cdr_reduce_samples_allreduce(p->peers, p->Z, 1, k, p->X, p->ldx, T, p->T_min, d, k,
+                                             p->P, peer::region_offset(*p->peers, p->WT), p->ldx,
+                                             p->state, s));
+    } else {
+        // W' = P Z'X  (gpnh_convex_coding.py:219-226)
+        CDR_TRY(cdr_reduce_samples(p->Z, 1, k, p->X, p->ldx, T, d, k, p->P, p->WT, p->ldx, w.stream,
+                                   w.stream_bytes, p->state, s));
+    }
 
-    if (!gpnh_fused_applicable(p, &TC, &nstrips)) {
+    if (!fused) {
         // general sequence (any k <= 64, any shape)
         CDR_TRY(gpnh_dictionary_products(p, w, false, s));
         CDR_TRY(cdr_gpnh_cost_check(p->state, p->cost_deltas, p->XWtZ, p->ZtZ, p->WtW, reg, k,
@@ -347,6 +367,12 @@ extern "C" int cdr_gpnh_iterate_enqueue(const cdr_gpnh_problem* p, cdr_stream_t 
     a.T = T; a.k = k; a.d = d; a.T_total = p->T_total;
     a.lambda_W = p->lambda_W;
     a.p = p->weights_params;
+    if (sharded) {
+        a.g = *p->peers;
+    } else {
+        a.g = cdr_peer_group();
+        a.g.world = 1;
+    }
     if (a.p.memory < 1 || a.p.memory > CDR_MAX_MEMORY) return CDR_ERR_UNSUPPORTED;
     int blocks;
     fused_grid(T, &a.spw, &blocks);

@@ -27,6 +27,7 @@
 // Other configurations (more inner SPG iterations, k > 16, small or Gram-space problems) run
 // the general kernel sequence of aa_steps.cu.  All reductions have a fixed order.
 #include "fused_weights.cuh"
+#include "peer.cuh"
 #include "small_solve.cuh"
 
 namespace cdr {
@@ -36,12 +37,20 @@ enum { RS_A0 = 0, RS_ROWMAX = 1, RS_DELTA = 2, RS_DD = 3, RS_A1 = 4, RS_BETA = 5
 
 constexpr int kAaRowMaxT = 26000;      // aa_steps.cu: rows are staged in shared memory
 
-// gradient entry (j, t):  s_g * (sum_i a_j a_i ZtZ[j][i] CK[i][t] - a_j KZt[j][t])
-__device__ __forceinline__ double aa_grad_entry(const cdr_aa_buffers& b, const double* coef, int j, int t)
+// gradient entry (j, t):  s_g * (sum_i a_j a_i ZtZ[j][i] CK[i][t] - a_j KZt[j][t]), k <= 16.
+// The k loads of the column are issued together (a loop with a run-time trip count would
+// serialise one L2 round trip per component); coef[i] = 0 for i >= k, and adding 0 * 0 leaves
+// the sum -- formed in the order i = 0, 1, ... as in aa_steps.cu -- unchanged.
+__device__ __forceinline__ double aa_grad_entry16(const cdr_aa_buffers& b, const double* coef, int j, int t)
 {
+    double ck[kFusedMaxK];
+#pragma unroll
+    for (int i = 0; i < kFusedMaxK; ++i) ck[i] = (i < b.k) ? b.CK[(long)i * b.ldt + t] : 0.0;
+    const double kz = b.KZt[(long)j * b.ldt + t];
     double s = 0.0;
-    for (int i = 0; i < b.k; ++i) s = fma(coef[i], b.CK[(long)i * b.ldt + t], s);
-    return b.grad_scale * (s - b.alpha[j] * b.KZt[(long)j * b.ldt + t]);
+#pragma unroll
+    for (int i = 0; i < kFusedMaxK; ++i) s = fma(coef[i], ck[i], s);
+    return b.grad_scale * (s - b.alpha[j] * kz);
 }
 
 // ---------------------------------------------------------------------- kernel 1
@@ -61,8 +70,8 @@ __global__ void __launch_bounds__(1024) aa_head_kernel(cdr_aa_buffers b, cdr_spg
 
     // x = project(x0) (spg.py:146-148) and the linear trace term a0 = a_j <x, (K Z)_j>
     for (int t = threadIdx.x; t < T; t += blockDim.x) work[t] = crow[t];
-    for (int i = threadIdx.x; i < k; i += blockDim.x)
-        coef[i] = b.alpha[j] * b.alpha[i] * b.ZtZ[j * k + i];
+    for (int i = threadIdx.x; i < kFusedMaxK; i += blockDim.x)
+        coef[i] = (i < k) ? b.alpha[j] * b.alpha[i] * b.ZtZ[j * k + i] : 0.0;
     __syncthreads();
     double th = block_simplex_threshold(work, 1, T, scratch);
     double a0[1] = {0.0};
@@ -75,10 +84,16 @@ __global__ void __launch_bounds__(1024) aa_head_kernel(cdr_aa_buffers b, cdr_spg
     if (threadIdx.x == 0) b.row_scratch[RS_A0 * k + j] = b.alpha[j] * a0[0];
 
     // g = df(x) (spg.py:176); work = x - g
-    for (int t = threadIdx.x; t < T; t += blockDim.x) {
-        const double g = aa_grad_entry(b, coef, j, t);
+    for (int t = threadIdx.x; t < T; t += 2 * blockDim.x) {
+        const int t2 = t + blockDim.x;
+        const double g = aa_grad_entry16(b, coef, j, t);
+        const double g2 = (t2 < T) ? aa_grad_entry16(b, coef, j, t2) : 0.0;
         grow[t] = g;
         work[t] = crow[t] - g;
+        if (t2 < T) {
+            grow[t2] = g2;
+            work[t2] = crow[t2] - g2;
+        }
     }
     const bool explicit_alpha = p.alpha0 > 0.0;        // spg.py:151; used unclamped when given
     if (!explicit_alpha) {
@@ -143,11 +158,29 @@ __global__ void __launch_bounds__(1024) aa_head_kernel(cdr_aa_buffers b, cdr_spg
 constexpr int kFinTB = 32;             // samples per CTA
 constexpr int kFinThreads = 1024;
 
+// Sample-sharded fit (g.world > 1): the block's columns of D K are pushed to every rank (the
+// k x T matrices are replicated), the k x k products are partial sums over this rank's
+// samples and the last CTA exchanges them with the other ranks before the line search, which
+// every rank then runs on identical numbers.
+struct AaFinalizeArgs {
+    cdr_aa_buffers b;        // b.T = all samples
+    cdr_spg_params p;
+    const double* part;      // [nstrips][Tl][KP] per-strip partials of (D X) X' for the local samples
+    int nstrips;
+    double* cta_part;
+    int Tl, row0;            // local samples: columns row0 .. row0 + Tl of the k x T matrices
+    cdr_peer_group g;
+    size_t dk_offset;        // of b.DK in the symmetric region (world > 1)
+};
+
 template <int KT>
-__global__ void __launch_bounds__(kFinThreads)
-aa_finalize_ls_kernel(cdr_aa_buffers b, cdr_spg_params p, const double* __restrict__ part,
-                      int nstrips, double* cta_part)
+__global__ void __launch_bounds__(kFinThreads) aa_finalize_ls_kernel(AaFinalizeArgs a)
 {
+    const cdr_aa_buffers& b = a.b;
+    const cdr_spg_params& p = a.p;
+    const double* __restrict__ part = a.part;
+    const int nstrips = a.nstrips;
+    double* cta_part = a.cta_part;
     cdr_loop_state* st = b.state;
     if (is_done(st)) return;
     constexpr int KP = 8 * KT;
@@ -159,9 +192,10 @@ aa_finalize_ls_kernel(cdr_aa_buffers b, cdr_spg_params p, const double* __restri
     __shared__ double2 red[GROUPS][ITEMS];             // 16 KB; re-used by the tail
     __shared__ double tiles[4][KP][kFinTB + 1];        // C, D, CK, DK
     __shared__ int is_last;
-    const int k = b.k, T = b.T;
+    const int k = b.k, T = a.Tl;
     const long ldt = b.ldt;
     const int t0 = blockIdx.x * kFinTB;
+    const bool sharded = a.g.world > 1;
 
     // ---- D K for this block of samples: sum of the per-strip partials, fixed order
     {
@@ -190,18 +224,27 @@ aa_finalize_ls_kernel(cdr_aa_buffers b, cdr_spg_params p, const double* __restri
             }
             const int j0 = 2 * pr;
             const bool ok = t < T;
-            if (ok && j0 < k) b.DK[(long)j0 * ldt + t] = a0;
-            if (ok && j0 + 1 < k) b.DK[(long)(j0 + 1) * ldt + t] = a1;
+            const long col = a.row0 + t;
+            if (!sharded) {
+                if (ok && j0 < k) b.DK[(long)j0 * ldt + col] = a0;
+                if (ok && j0 + 1 < k) b.DK[(long)(j0 + 1) * ldt + col] = a1;
+            } else {
+                for (int r = 0; r < a.g.world; ++r) {
+                    double* dk = peer::peer_ptr<double>(a.g, r, a.dk_offset);
+                    if (ok && j0 < k) dk[(long)j0 * ldt + col] = a0;
+                    if (ok && j0 + 1 < k) dk[(long)(j0 + 1) * ldt + col] = a1;
+                }
+            }
             tiles[3][j0][tl] = (ok && j0 < k) ? a0 : 0.0;
             tiles[3][j0 + 1][tl] = (ok && j0 + 1 < k) ? a1 : 0.0;
         }
     }
     for (int idx = threadIdx.x; idx < 3 * KP * kFinTB; idx += blockDim.x) {
-        const int a = idx / (KP * kFinTB), rem = idx % (KP * kFinTB);
+        const int which = idx / (KP * kFinTB), rem = idx % (KP * kFinTB);
         const int i = rem / kFinTB, tl = rem % kFinTB;
         const int t = t0 + tl;
-        const double* src = (a == 0) ? b.C : (a == 1) ? b.D : b.CK;
-        tiles[a][i][tl] = (i < k && t < T) ? src[(long)i * ldt + t] : 0.0;
+        const double* src = (which == 0) ? b.C : (which == 1) ? b.D : b.CK;
+        tiles[which][i][tl] = (i < k && t < T) ? src[(long)i * ldt + a.row0 + t] : 0.0;
     }
     __syncthreads();
 
@@ -215,7 +258,8 @@ aa_finalize_ls_kernel(cdr_aa_buffers b, cdr_spg_params p, const double* __restri
         for (int tl = 0; tl < kFinTB; ++tl) s = fma(left[tl], right[tl], s);
         __stcg(cta_part + (long)blockIdx.x * NOUT + o, s);
     }
-    __threadfence();
+    if (sharded) __threadfence_system();          // the pushed columns of D K
+    else __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(&st->tickets[3], 1u) == gridDim.x - 1) ? 1 : 0;
     __syncthreads();
@@ -246,6 +290,9 @@ aa_finalize_ls_kernel(cdr_aa_buffers b, cdr_spg_params p, const double* __restri
         }
         __syncthreads();
     }
+    // sample-sharded fit: sum over ranks (also the barrier after which every rank's columns
+    // of D K have arrived here)
+    if (sharded) peer::cta_allreduce_small(a.g, fin, NOUT);
     const double* G00 = fin;
     const double* G01 = fin + KP * KP;
     const double* G11 = fin + 2 * KP * KP;
@@ -264,14 +311,19 @@ aa_finalize_ls_kernel(cdr_aa_buffers b, cdr_spg_params p, const double* __restri
         q1 = warp_sum(q1);
         q2 = warp_sum(q2);
         double lam = 1.0;
+        // row partials of the head kernel: one row per lane, summed in row order
+        const double ra0 = (lane < k) ? b.row_scratch[RS_A0 * k + lane] : 0.0;
+        const double rdl = (lane < k) ? b.row_scratch[RS_DELTA * k + lane] : 0.0;
+        const double rdd = (lane < k) ? b.row_scratch[RS_DD * k + lane] : 0.0;
+        const double ra1 = (lane < k) ? b.row_scratch[RS_A1 * k + lane] : 0.0;
+        double a0 = 0.0, delta = 0.0, dd = 0.0, a1 = 0.0;
+        for (int j = 0; j < k; ++j) {
+            a0 += __shfl_sync(CDR_FULL_MASK, ra0, j);
+            delta += __shfl_sync(CDR_FULL_MASK, rdl, j);
+            dd += __shfl_sync(CDR_FULL_MASK, rdd, j);
+            a1 += __shfl_sync(CDR_FULL_MASK, ra1, j);
+        }
         if (lane == 0) {
-            double a0 = 0.0, delta = 0.0, dd = 0.0, a1 = 0.0;
-            for (int j = 0; j < k; ++j) {
-                a0 += b.row_scratch[RS_A0 * k + j];
-                delta += b.row_scratch[RS_DELTA * k + j];
-                dd += b.row_scratch[RS_DD * k + j];
-                a1 += b.row_scratch[RS_A1 * k + j];
-            }
             const double tr = st->trace_data, sf = b.cost_scale;
             // f(x) at the start of spg() (spg.py:153-157); the memory starts as zeros
             const double f_old = 0.5 * (tr - 2.0 * a0 + q0) * sf;
@@ -302,7 +354,7 @@ aa_finalize_ls_kernel(cdr_aa_buffers b, cdr_spg_params p, const double* __restri
             st->spg_feval = feval + 1;
             // cost after the dictionary update (archetypal_analysis.py:623-630)
             const double cost = 0.5 * (tr - 2.0 * (a0 + lam * a1) + (q0 + lam * q1 + lam * lam * q2)) /
-                                (double)T;
+                                (double)b.T;
             finish_sub_step(st, b.cost_deltas, cost, 2, 0);
             st->tickets[3] = 0u;
         }
@@ -318,11 +370,13 @@ aa_finalize_ls_kernel(cdr_aa_buffers b, cdr_spg_params p, const double* __restri
 
 // ---------------------------------------------------------------------- kernel 5
 struct AaWeightsArgs {
-    cdr_aa_buffers b;
-    double* Z;
+    cdr_aa_buffers b;        // b.T = all samples
+    double* Z;               // Tl x k: the local samples
     double* cta_part;
     int spw;
+    int Tl, row0;
     cdr_spg_params p;
+    cdr_peer_group g;        // world == 1: single GPU
 };
 
 template <int KPL>
@@ -338,10 +392,26 @@ __global__ void __launch_bounds__(kFusedThreads) aa_weights_fused_kernel(AaWeigh
     double* wsum = fsm + (KPL > 1 ? KP * KP : 0);   // [kFusedWarps][NST]
     double* fin = wsum + kFusedWarps * NST;         // 4 * NST
 
-    const int k = b.k, T = b.T;
+    const int k = b.k, T = a.Tl;
     const long ldt = b.ldt;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane & 7, q = lane >> 3;
+    const double lam = st->lam;
+
+    // sample-sharded fit: the dictionary and C K are replicated, so the columns of the other
+    // ranks' samples are updated here as well (their D K has arrived: barrier in kernel 4)
+    if (a.g.world > 1) {
+        const long total = (long)k * b.T;
+        for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+             idx += (long)gridDim.x * blockDim.x) {
+            const int i = (int)(idx / b.T), col = (int)(idx % b.T);
+            if (col < a.row0 || col >= a.row0 + T) {
+                const long e = (long)i * ldt + col;
+                b.C[e] = fma(lam, b.D[e], b.C[e]);
+                b.CK[e] = fma(lam, b.DK[e], b.CK[e]);
+            }
+        }
+    }
 
     // A' = D (C K C') D  (archetypal_analysis.py:384-385)
     if constexpr (KPL > 1) {
@@ -363,36 +433,44 @@ __global__ void __launch_bounds__(kFusedThreads) aa_weights_fused_kernel(AaWeigh
     const bool has_sample = t_raw < T;
     const bool valid = (q < spw) && has_sample;
     const long t = has_sample ? t_raw : (T - 1);
-    const double lam = st->lam;
+    const long col = a.row0 + t;
 
     // x <- x + lam d, C K <- C K + lam D K for this sample's column (spg.py:219; linearity
     // of C -> C K), then the linear term b = -D (C K)[:, t]
-    double z0[KPL], x[KPL], bl[KPL], ck[KPL];
+    double z0[KPL], x[KPL], bl[KPL], ck[KPL], cn[KPL], ckn[KPL];
     bool present[KPL];
 #pragma unroll
     for (int r = 0; r < KPL; ++r) {
         const int c = g * KPL + r;
         present[r] = c < k;
         if (present[r]) {
-            const long idx = (long)c * ldt + t;
-            const double cn = fma(lam, b.D[idx], b.C[idx]);
-            const double ckn = fma(lam, b.DK[idx], b.CK[idx]);
-            if (valid) {
-                b.C[idx] = cn;
-                b.CK[idx] = ckn;
-            }
-            ck[r] = b.alpha[c] * ckn;
+            const long idx = (long)c * ldt + col;
+            cn[r] = fma(lam, b.D[idx], b.C[idx]);
+            ckn[r] = fma(lam, b.DK[idx], b.CK[idx]);
+            ck[r] = b.alpha[c] * ckn[r];
             bl[r] = -ck[r];
             z0[r] = a.Z[t * k + c];
         } else {
-            ck[r] = 0.0;
+            cn[r] = ckn[r] = ck[r] = 0.0;
             bl[r] = 0.0;
             z0[r] = -INFINITY;
         }
     }
+    // the replicas of a sample (lane groups >= spw) have read the same column: store only
+    // after every lane of the warp has loaded
+    __syncwarp();
+    if (valid) {
+#pragma unroll
+        for (int r = 0; r < KPL; ++r)
+            if (present[r]) {
+                const long idx = (long)(g * KPL + r) * ldt + col;
+                b.C[idx] = cn[r];
+                b.CK[idx] = ckn[r];
+            }
+    }
 
     int n_iter = 0, n_feval = 0;
-    qp_solve<KPL>(As, arow, z0, bl, present, a.p, valid, g, x, n_iter, n_feval);
+    qp_solve<KPL>(As, arow, z0, bl, present, a.p, has_sample, g, spw, x, n_iter, n_feval);
 
     double tr_new = 0.0;
     if (valid) {
@@ -409,6 +487,7 @@ __global__ void __launch_bounds__(kFusedThreads) aa_weights_fused_kernel(AaWeigh
                                       &st->tickets[1]))
         return;
     fused_final_sum<KPL>(a.cta_part, fin);
+    if (a.g.world > 1) peer::cta_allreduce_small(a.g, fin, NST);
     // fin[i * KP + j] = (Z'Z)[i][j]; fin[KP * KP + 1] = sum_i a_i (C K Z)[i][i]
     if (warp == 0) {
         double t2 = 0.0;
@@ -419,7 +498,7 @@ __global__ void __launch_bounds__(kFusedThreads) aa_weights_fused_kernel(AaWeigh
         t2 = warp_sum(t2);
         if (lane == 0) {
             // cost after the weights update (archetypal_analysis.py:645-652), stopping rule
-            const double cost = 0.5 * (st->trace_data - 2.0 * fin[KP * KP + 1] + t2) / (double)T;
+            const double cost = 0.5 * (st->trace_data - 2.0 * fin[KP * KP + 1] + t2) / (double)b.T;
             finish_sub_step(st, b.cost_deltas, cost, 3, 1);
             if (!st->done) st->old_cost = st->cost;    // start of the next iteration
             st->tickets[1] = 0u;
@@ -427,6 +506,70 @@ __global__ void __launch_bounds__(kFusedThreads) aa_weights_fused_kernel(AaWeigh
     }
     for (int idx = threadIdx.x; idx < k * k; idx += blockDim.x)
         b.ZtZ[idx] = fin[(idx / k) * KP + idx % k];
+}
+
+// ---------------------------------------------------------------------- kernel 8 (sharded)
+// out[j][col0 + t] = sum over strips of part[strip][t][j] for the local samples t, written to
+// EVERY rank (the k x T matrix is replicated); the last CTA then meets the other ranks, after
+// which all columns of `out` are complete on this rank.  Same summation order as
+// reduce_features_strip_finalize_kernel.
+template <int KT>
+__global__ void __launch_bounds__(256)
+features_finalize_push_kernel(const double* __restrict__ part, int Tl, int nstrips, int k,
+                              size_t out_offset, long ldo, int col0, cdr_peer_group g,
+                              cdr_loop_state* st)
+{
+    if (is_done(st)) return;
+    constexpr int KP = 8 * KT;
+    constexpr int PAIRS = KP / 2;
+    __shared__ double2 red[8][32];
+    __shared__ int is_last;
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const long item = (long)blockIdx.x * 32 + lane;
+    const long nitems = (long)Tl * PAIRS;
+    const long stride = nitems;
+    const int per = (nstrips + 7) / 8;
+    double s0 = 0.0, s1 = 0.0;
+    if (item < nitems) {
+        const double2* src = reinterpret_cast<const double2*>(part) + item;
+        const int hi = min(nstrips, (grp + 1) * per);
+        int sidx = grp * per;
+        for (; sidx + 2 <= hi; sidx += 2) {
+            const double2 v0 = src[(long)sidx * stride];
+            const double2 v1 = src[(long)(sidx + 1) * stride];
+            s0 += v0.x; s1 += v0.y;
+            s0 += v1.x; s1 += v1.y;
+        }
+        for (; sidx < hi; ++sidx) {
+            const double2 v = src[(long)sidx * stride];
+            s0 += v.x;
+            s1 += v.y;
+        }
+    }
+    red[grp][lane] = make_double2(s0, s1);
+    __syncthreads();
+    if (grp == 0 && item < nitems) {
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            a0 += red[q][lane].x;
+            a1 += red[q][lane].y;
+        }
+        const int t = (int)(item / PAIRS), j = 2 * (int)(item % PAIRS);
+        for (int r = 0; r < g.world; ++r) {
+            double* out = peer::peer_ptr<double>(g, r, out_offset);
+            if (j < k) out[(long)j * ldo + col0 + t] = a0;
+            if (j + 1 < k) out[(long)(j + 1) * ldo + col0 + t] = a1;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&st->tickets[0], 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    peer::cta_allreduce_small(g, nullptr, 0);
+    if (threadIdx.x == 0) st->tickets[0] = 0u;
 }
 
 static size_t aa_fused_smem_bytes(int kp)
@@ -486,11 +629,18 @@ static bool aa_fused_shape(int T, int d, int k, int dict_max_iterations, int* ns
     return features_strip_geometry(T, d, k, &TC, nstrips);
 }
 
+static bool aa_sharded(const cdr_aa_problem* p) { return p->peers != nullptr && p->peers->world > 1; }
+
 static int check_aa(const cdr_aa_problem* p)
 {
     CDR_CHECK_ARG(p != nullptr && p->X != nullptr && p->Z != nullptr && p->tmp_kd != nullptr);
     const cdr_aa_buffers& b = p->buf;
-    CDR_CHECK_ARG(b.k >= 1 && b.T >= 1 && p->T == b.T && p->d >= 1 && b.ldt >= b.T);
+    CDR_CHECK_ARG(b.k >= 1 && b.T >= 1 && p->T >= 1 && p->d >= 1 && b.ldt >= b.T);
+    if (aa_sharded(p)) {
+        CDR_CHECK_ARG(p->row0 >= 0 && p->row0 + p->T <= b.T && p->T_min >= 1 && p->T_min <= p->T);
+    } else {
+        CDR_CHECK_ARG(p->T == b.T && p->row0 == 0);
+    }
     CDR_CHECK_ARG(b.C && b.G && b.D && b.CK && b.DK && b.KZt && b.alpha && b.ZtZ && b.CKCt &&
                   b.CKZ && b.G01 && b.G11 && b.row_scratch && b.state);
     if (b.k > CDR_MAX_COMPONENTS || b.T > kAaRowMaxT) return CDR_ERR_UNSUPPORTED;
@@ -546,6 +696,8 @@ extern "C" int cdr_aa_fused_applicable(int T, int d, int k, int dictionary_max_i
 extern "C" int cdr_aa_prepare_enqueue(const cdr_aa_problem* p, cdr_stream_t stream)
 {
     CDR_TRY(check_aa(p));
+    // sample-sharded fits: the caller forms the initial products with its own collectives
+    if (aa_sharded(p)) return CDR_ERR_UNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
     const cdr_aa_buffers& b = p->buf;
     const int k = b.k;
@@ -581,8 +733,16 @@ extern "C" int cdr_aa_iterate_enqueue(const cdr_aa_problem* p, cdr_stream_t stre
         p->weights_params.memory > CDR_MAX_MEMORY)
         return CDR_ERR_UNSUPPORTED;
     int nstrips = 0;
+    const bool sharded = aa_sharded(p);
+    const bool fused = aa_fused_shape(sharded ? p->T_min : T, d, k, dp.max_iterations, &nstrips) &&
+                       b.T <= kAaRowMaxT;
+    // over peer memory only the eight-kernel path is offered
+    if (sharded && !fused) return CDR_ERR_UNSUPPORTED;
+    cdr_peer_group grp = cdr_peer_group();
+    grp.world = 1;
+    if (sharded) grp = *p->peers;
 
-    if (!aa_fused_shape(T, d, k, dp.max_iterations, &nstrips)) {
+    if (!fused) {
         // general sequence (archetypal_analysis.py:586-663 with the pieces of aa_steps.cu)
         CDR_TRY(cdr_loop_begin(b.state, s));
         CDR_TRY(cdr_aa_spg_begin(&b, &dp, s));
@@ -608,14 +768,22 @@ extern "C" int cdr_aa_iterate_enqueue(const cdr_aa_problem* p, cdr_stream_t stre
 
     // 1. head: projection, gradient, first step length, direction
     {
-        const size_t smem = (64 + CDR_MAX_COMPONENTS + (size_t)T) * sizeof(double);
+        // the rows of the (replicated) dictionary span all samples
+        const size_t smem = (64 + CDR_MAX_COMPONENTS + (size_t)b.T) * sizeof(double);
         CDR_TRY(ensure_dyn_smem<aa_head_kernel>(smem));
-        aa_head_kernel<<<k, aa_row_threads(T), smem, s>>>(b, dp);
+        aa_head_kernel<<<k, aa_row_threads(b.T), smem, s>>>(b, dp);
         CDR_RETURN_IF_LAUNCH_FAILED();
     }
-    // 2. D X    3. (D X) X' as per-strip partials
-    CDR_TRY(cdr_reduce_samples(b.D, b.ldt, 1, p->X, p->ldx, T, d, k, nullptr, p->tmp_kd, p->ldx,
-                               w.stream, w.stream_bytes, b.state, s));
+    // 2. D X (summed over ranks in the kernel's epilogue when sharded)
+    // 3. (D X) X' as per-strip partials
+    if (sharded) {
+        CDR_TRY(cdr_reduce_samples_allreduce(p->peers, b.D + p->row0, b.ldt, 1, p->X, p->ldx, T,
+                                             p->T_min, d, k, nullptr,
+                                             peer::region_offset(grp, p->tmp_kd), p->ldx, b.state, s));
+    } else {
+        CDR_TRY(cdr_reduce_samples(b.D, b.ldt, 1, p->X, p->ldx, T, d, k, nullptr, p->tmp_kd, p->ldx,
+                                   w.stream, w.stream_bytes, b.state, s));
+    }
     {
         const int rc = run_reduce_features_tma(p->tmp_kd, p->ldx, p->X, p->ldx, T, d, k, nullptr, 0,
                                                w.stream, w.stream_bytes, b.state, s, nullptr);
@@ -623,11 +791,19 @@ extern "C" int cdr_aa_iterate_enqueue(const cdr_aa_problem* p, cdr_stream_t stre
     }
     // 4. D K, the k x k products, line search, cost check after the dictionary update
     {
+        AaFinalizeArgs fa;
+        fa.b = b;
+        fa.p = dp;
+        fa.part = w.stream;
+        fa.nstrips = nstrips;
+        fa.cta_part = w.fin_part;
+        fa.Tl = T;
+        fa.row0 = p->row0;
+        fa.g = grp;
+        fa.dk_offset = sharded ? peer::region_offset(grp, b.DK) : 0;
         const int blocks = (T + kFinTB - 1) / kFinTB;
-        if (k <= 8)
-            aa_finalize_ls_kernel<1><<<blocks, kFinThreads, 0, s>>>(b, dp, w.stream, nstrips, w.fin_part);
-        else
-            aa_finalize_ls_kernel<2><<<blocks, kFinThreads, 0, s>>>(b, dp, w.stream, nstrips, w.fin_part);
+        if (k <= 8) aa_finalize_ls_kernel<1><<<blocks, kFinThreads, 0, s>>>(fa);
+        else aa_finalize_ls_kernel<2><<<blocks, kFinThreads, 0, s>>>(fa);
         CDR_RETURN_IF_LAUNCH_FAILED();
     }
     // 5. per-sample QPs with the update of C, C K and the statistics
@@ -637,6 +813,9 @@ extern "C" int cdr_aa_iterate_enqueue(const cdr_aa_problem* p, cdr_stream_t stre
         a.Z = p->Z;
         a.cta_part = w.cta_part;
         a.p = p->weights_params;
+        a.Tl = T;
+        a.row0 = p->row0;
+        a.g = grp;
         int blocks;
         fused_grid(T, &a.spw, &blocks);
         if (k <= 8) {
@@ -651,5 +830,26 @@ extern "C" int cdr_aa_iterate_enqueue(const cdr_aa_problem* p, cdr_stream_t stre
         CDR_RETURN_IF_LAUNCH_FAILED();
     }
     // 6.-8. (K Z)' for the next dictionary step
-    return aa_apply_right(p, w, s);
+    if (!sharded) return aa_apply_right(p, w, s);
+    CDR_TRY(cdr_reduce_samples_allreduce(p->peers, p->Z, 1, k, p->X, p->ldx, T, p->T_min, d, k, nullptr,
+                                         peer::region_offset(grp, p->tmp_kd), p->ldx, b.state, s));
+    {
+        const int rc = run_reduce_features_tma(p->tmp_kd, p->ldx, p->X, p->ldx, T, d, k, nullptr, 0,
+                                               w.stream, w.stream_bytes, b.state, s, nullptr);
+        if (rc != 0) return rc == CDR_TMA_NOT_APPLICABLE ? CDR_ERR_UNSUPPORTED : rc;
+    }
+    {
+        const int kp = (k <= 8) ? 8 : 16;
+        const long nitems = (long)T * (kp / 2);
+        const int blocks = (int)((nitems + 31) / 32);
+        const size_t off = peer::region_offset(grp, b.KZt);
+        if (k <= 8)
+            features_finalize_push_kernel<1><<<blocks, 256, 0, s>>>(w.stream, T, nstrips, k, off, b.ldt,
+                                                                    p->row0, grp, b.state);
+        else
+            features_finalize_push_kernel<2><<<blocks, 256, 0, s>>>(w.stream, T, nstrips, k, off, b.ldt,
+                                                                    p->row0, grp, b.state);
+        CDR_RETURN_IF_LAUNCH_FAILED();
+    }
+    return 0;
 }

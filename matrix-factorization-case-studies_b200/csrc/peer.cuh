@@ -40,10 +40,16 @@ struct PeerHeader {
     unsigned long long ready[CDR_PEER_MAX_STRIPS][CDR_MAX_PEERS];      // [strip][from rank]
     unsigned long long done[CDR_PEER_MAX_STRIPS];
     int error;                                           // 0, or the wait that timed out
+    int reserved2_;
+    // one-shot exchanges of small vectors by the tails of the fused iteration kernels
+    // (cta_allreduce_small): two slot sets used alternately, one slot and one flag per peer
+    unsigned long long small_epoch;
+    unsigned long long small_flag[2][CDR_MAX_PEERS];
+    double small_slot[2][CDR_MAX_PEERS][CDR_PEER_SMALL_MAX];
 };
 static_assert(sizeof(PeerHeader) <= CDR_PEER_HEADER_BYTES, "peer header does not fit");
 
-enum PeerWait { kWaitStart = 1, kWaitFinish = 2, kWaitReady = 3, kWaitDone = 4 };
+enum PeerWait { kWaitStart = 1, kWaitFinish = 2, kWaitReady = 3, kWaitDone = 4, kWaitSmall = 5 };
 
 __device__ __forceinline__ PeerHeader* header_of(const cdr_peer_group& g, int r)
 {
@@ -119,6 +125,56 @@ __device__ __forceinline__ void cta_barrier_all_ranks(const cdr_peer_group& g,
         wait_flag(local, epoch, mine, WHICH);
     }
     __syncthreads();
+}
+
+// In-place sum over ranks of the n <= CDR_PEER_SMALL_MAX doubles vals[0..n) (shared or global
+// memory of the calling CTA), executed by ONE CTA per rank -- the last CTA of a fused kernel,
+// after it has reduced its own rank's partials.  One shot: every rank pushes its vector into
+// slot[rank] of every peer, raises a flag there, waits for the flags of all peers and sums the
+// slots in rank order (so every rank gets the same bits).  Doubles as a barrier between the
+// ranks (n = 0): data pushed to peer memory by the calling kernel before this call -- by any
+// of its CTAs, provided they fenced at system scope before the caller learnt it is last --
+// has arrived when it returns.  Two slot sets alternate: a rank can be at most one exchange
+// ahead of its peers (it cannot finish exchange e + 1 before every peer has entered it, i.e.
+// has finished reading exchange e).  All threads of the CTA must call this.
+__device__ __forceinline__ void cta_allreduce_small(const cdr_peer_group& g, double* vals, int n)
+{
+    PeerHeader* mine = header_of(g, g.rank);
+    const unsigned long long epoch = *((volatile unsigned long long*)&mine->small_epoch) + 1;
+    const int set = (int)(epoch & 1ull);
+    for (int r = 0; r < g.world; ++r) {
+        double* dst = header_of(g, r)->small_slot[set][g.rank];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = vals[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < g.world) {
+        const int p = threadIdx.x;
+        st_release_sys(&header_of(g, p)->small_flag[set][g.rank], epoch);
+        wait_flag(&mine->small_flag[set][p], epoch, mine, kWaitSmall);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double s = ld_sys_d(&mine->small_slot[set][0][i]);
+        for (int r = 1; r < g.world; ++r) s += ld_sys_d(&mine->small_slot[set][r][i]);
+        vals[i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *((volatile unsigned long long*)&mine->small_epoch) = epoch;
+}
+
+// byte offset of a local pointer inside this rank's region
+__device__ __host__ __forceinline__ size_t region_offset(const cdr_peer_group& g, const void* p)
+{
+    return (size_t)(static_cast<const unsigned char*>(p) -
+                    static_cast<const unsigned char*>(g.region[g.rank]));
+}
+
+// the same location in the region of rank r
+template <class T>
+__device__ __forceinline__ T* peer_ptr(const cdr_peer_group& g, int r, size_t offset)
+{
+    return reinterpret_cast<T*>(static_cast<unsigned char*>(g.region[r]) + offset);
 }
 
 // Arguments of the fused reduce-over-samples + all-reduce kernel (stream_tma.cu).

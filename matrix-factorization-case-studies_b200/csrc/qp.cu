@@ -48,9 +48,12 @@ qp_batched_kernel(const double* __restrict__ A, const double* __restrict__ alpha
     const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     // spw samples per warp (1, 2 or 4): small batches use one sample per warp so that no
     // sample waits in lock step for a slower neighbour (the kernel is latency bound)
-    const int t_raw = warp_global * spw + (lane >> 3);
-    const bool valid = ((lane >> 3) < spw) && (t_raw < T);
-    const long t = valid ? t_raw : (T - 1);
+    // lane group q works on sample q % spw of the warp: with spw < 4 the remaining groups are
+    // replicas, which share the line-search trials of their sample (qp_core.cuh)
+    const int t_raw = warp_global * spw + ((lane >> 3) % spw);
+    const bool has_sample = t_raw < T;
+    const bool valid = ((lane >> 3) < spw) && has_sample;
+    const long t = has_sample ? t_raw : (T - 1);
 
     double arow[8];
     if constexpr (KPL == 1) {
@@ -82,7 +85,7 @@ qp_batched_kernel(const double* __restrict__ A, const double* __restrict__ alpha
     }
 
     int n_iter = 0, n_feval = 0;
-    qp_solve<KPL>(As, arow, tmp, b, present, p, valid, g, x, n_iter, n_feval);
+    qp_solve<KPL>(As, arow, tmp, b, present, p, has_sample, g, spw, x, n_iter, n_feval);
 
     if (valid) {
 #pragma unroll

@@ -58,14 +58,21 @@ struct QpMatVec {
 //   z0        : the sample's initial guess (absent components = -inf), x receives the result
 //   b         : linear term of the lane's components (0 on absent components)
 //   valid     : group-uniform; groups without a sample run along with frozen state
+//   spw       : samples per warp (1, 2 or 4).  Lane group q works on sample q % spw of the
+//               warp; the 4 / spw groups with the same sample are exact replicas of each
+//               other (the callers load them identically) and share the line-search trials.
 // All 32 lanes of the warp must call this together.
 template <int KPL>
 __device__ __forceinline__ void qp_solve(const double* As, const double (&arow)[8],
                                          const double (&z0)[KPL], const double (&b)[KPL],
                                          const bool (&present)[KPL], const cdr_spg_params& p,
-                                         bool valid, int g, double (&x)[KPL], int& n_iter_out,
-                                         int& n_feval_out)
+                                         bool valid, int g, int spw, double (&x)[KPL],
+                                         int& n_iter_out, int& n_feval_out)
 {
+    const int lane_group = (threadIdx.x & 31) >> 3;
+    const int sample_group = lane_group % spw;           // first lane group of this sample
+    const int replica = lane_group / spw;
+    const int replicas = 4 / spw;
     double Ax[KPL], gk[KPL], dk[KPL], xo[KPL], tmp[KPL], prj[KPL];
 #pragma unroll
     for (int r = 0; r < KPL; ++r) tmp[r] = z0[r];
@@ -155,16 +162,23 @@ __device__ __forceinline__ void qp_solve(const double* As, const double (&arow)[
         int fe = 1;
         bool searching = active && (f_new > f_max + p.gamma * lam * delta);
         // Backtracking.  Once sigma_two * lam < sigma_one the safeguarded interpolation of
-        // spg.py:19-33 can only return lam / 2 (its acceptance interval is empty), so the next
-        // four trial steps are known in advance: they are evaluated together (four independent
-        // 8-lane reductions in flight instead of one) and then examined in order, exactly as
-        // the reference would.  This is where the samples with rounding-level Armijo failures
-        // spend their time (~33 halvings per iteration down to lambda_min).
+        // spg.py:19-33 can only return lam / 2 (its acceptance interval is empty), so the
+        // following trial steps l0, l0/2, l0/4, ... are known in advance.  They are evaluated
+        // 4 * replicas at a time -- four per lane group (four independent 8-lane reductions in
+        // flight), and when several lane groups of the warp hold the same sample (small
+        // batches: one sample per warp, see the callers) each replica takes its own four --
+        // and then examined in order, exactly as the reference would.  This is where the
+        // samples with rounding-level Armijo failures spend their time (~33 halvings per
+        // iteration down to lambda_min); every replica forms its sums in the same order, so
+        // the result does not depend on the number of replicas.
         while (__any_sync(CDR_FULL_MASK, searching)) {
             const bool halving = p.sigma_two * lam < p.sigma_one;
+            const double l0 = searching ? spg_step_length(lam, delta, f_old, f_new, p.sigma_one,
+                                                          p.sigma_two)
+                                        : lam;
+            const int first = halving ? 4 * replica : 0;         // this group's first trial
             double lt[4];
-            lt[0] = searching ? spg_step_length(lam, delta, f_old, f_new, p.sigma_one, p.sigma_two)
-                              : lam;
+            lt[0] = l0 * (1.0 / (double)(1 << first));           // exact power-of-two scaling
             lt[1] = 0.5 * lt[0];
             lt[2] = 0.5 * lt[1];
             lt[3] = 0.5 * lt[2];
@@ -182,16 +196,31 @@ __device__ __forceinline__ void qp_solve(const double* As, const double (&arow)[
 #pragma unroll
                 for (int j = 0; j < 4; ++j) st[j] += __shfl_xor_sync(CDR_FULL_MASK, st[j], o, 8);
             }
+            // first trial of this group at which the search ends (step below lambda_min, or
+            // the Armijo condition holds): 99 = none
             const int nvalid = halving ? 4 : 1;
+            int stop = 99;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (j < nvalid && searching) {
-                    lam = lt[j];
-                    f_new = st[j];
-                    fe += 1;
-                    if (fabs(lam) < p.lambda_min) searching = false;
-                    else searching = f_new > f_max + p.gamma * lam * delta;
-                }
+            for (int j = 3; j >= 0; --j) {
+                const bool ends = (fabs(lt[j]) < p.lambda_min) ||
+                                  !(st[j] > f_max + p.gamma * lt[j] * delta);
+                if (j < nvalid && ends) stop = first + j;
+            }
+            // earliest such trial over the replicas of the sample
+            int m = stop;
+            for (int rho = 0; rho < replicas; ++rho)
+                m = min(m, __shfl_sync(CDR_FULL_MASK, stop, (sample_group + spw * rho) * 8 + g));
+            const int round_trials = halving ? 4 * replicas : 1;
+            const int last = (m == 99) ? round_trials - 1 : m;   // the trial the search is at now
+            const int jsel = last & 3;
+            const double fsel = (jsel == 0) ? st[0] : (jsel == 1) ? st[1] : (jsel == 2) ? st[2] : st[3];
+            const double f_at = __shfl_sync(CDR_FULL_MASK, fsel,
+                                            (sample_group + spw * (halving ? last >> 2 : 0)) * 8 + g);
+            if (searching) {
+                lam = l0 * (1.0 / (double)(1 << last));
+                f_new = f_at;
+                fe += last + 1;
+                searching = (m == 99);
             }
         }
 #pragma unroll

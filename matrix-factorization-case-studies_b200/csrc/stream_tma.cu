@@ -304,6 +304,12 @@ reduce_samples_tma_kernel(const double* __restrict__ Lp, long sLi, long sLt,
 // double-buffered shared-memory exchange (one 256-thread named barrier per stage) and
 // written as the strip's partial out[strip][t][j]; the strips are summed in fixed order by
 // reduce_features_strip_finalize_kernel.
+// The rows are walked BOTTOM-UP.  In an outer iteration the passes over X alternate -- reduce
+// over samples (top-down; its summation order over t fixes the rounding, so it stays), then
+// this kernel -- and X (570 MB at HadISST shape) is several times the 126 MB L2: walking the
+// other way round, each pass starts on the rows the previous pass read last, which are still
+// L2-resident, instead of on the rows that were evicted first.  The results do not depend on
+// the row order (every sample is reduced on its own).
 constexpr int kFsTR = 16;
 
 __device__ __forceinline__ void consumer_barrier()
@@ -346,7 +352,8 @@ reduce_features_strip_kernel(const double* __restrict__ M, long ldm, const doubl
             for (int rt = 0; rt < ntiles; ++rt, ++it) {
                 const int s = it % stages;
                 const uint32_t ph = (uint32_t)(it / stages) & 1u;
-                const int rows = min(kFsTR, T - rt * kFsTR);
+                const int tile = ntiles - 1 - rt;          // bottom-up: see the kernel comment
+                const int rows = min(kFsTR, T - tile * kFsTR);
                 if (lane == 0) {
                     mbar_wait(&pipe.empty[s], ph ^ 1u);
                     mbar_arrive_expect_tx(&pipe.full[s], (uint32_t)(rows * w * 8));
@@ -354,7 +361,7 @@ reduce_features_strip_kernel(const double* __restrict__ M, long ldm, const doubl
                 __syncwarp();
                 if (lane < rows)
                     bulk_g2s(tiles + s * stage_doubles + (long)lane * RS,
-                             X + (long)(rt * kFsTR + lane) * ldx + c0, (uint32_t)(w * 8),
+                             X + (long)(tile * kFsTR + lane) * ldx + c0, (uint32_t)(w * 8),
                              &pipe.full[s]);
             }
         }
@@ -428,7 +435,7 @@ reduce_features_strip_kernel(const double* __restrict__ M, long ldm, const doubl
         for (int rt = 0; rt < ntiles; ++rt, ++it) {
             const int s = it % stages;
             const uint32_t ph = (uint32_t)(it / stages) & 1u;
-            const int t = rt * kFsTR + 8 * mt + lc;
+            const int t = (ntiles - 1 - rt) * kFsTR + 8 * mt + lc;
             const bool rowok = t < T;
             double acc[KT][2];
 #pragma unroll

@@ -7,11 +7,11 @@
 // f64 kind), so the kernel is a classic multi-stage pipeline around it:
 //   * CTA tile 128 x 128, eight warps as 2 (rows) x 4 (columns), warp tile 64 x 32
 //     = 8 x 4 DMMA tiles, 64 fp64 accumulators per thread;
-//   * both operands are row blocks of X; a stage holds 128 x 32 doubles of each, copied
-//     global -> shared with 16-byte cp.async (LDGSTS) -- 256-byte row segments are too short
-//     for bulk copies to pay (profiles/probes/tma_probe.cu) and the pipe only needs ~8 B /
-//     cycle / SM; rows are padded to 40 doubles so that the 16-byte fragment reads of a
-//     quarter warp fall into distinct banks; diagonal tiles load one operand only;
+//   * both operands are row blocks of X; a stage holds 128 x 16 doubles of each (four stages,
+//     192 KB), copied global -> shared with 16-byte cp.async (LDGSTS) -- 128-byte row segments
+//     are far too short for bulk copies to pay (profiles/probes/tma_probe.cu) and the pipe
+//     only needs ~8 B / cycle / SM; rows are padded to 24 doubles so that the 16-byte fragment
+//     reads of a quarter warp fall into distinct banks; diagonal tiles load one operand only;
 //   * fragment trick of the streaming kernels: the reduction index of an MMA can be permuted
 //     freely, so each lane loads a double2 and feeds .x / .y to two MMAs;
 //   * the feature axis is split so that (tiles x splits) fills whole waves of SMs; every
@@ -22,12 +22,13 @@
 namespace cdr {
 
 constexpr int kSyrkTile = 128;
-constexpr int kSyrkKC = 32;                   // doubles of the feature axis per stage
+constexpr int kSyrkKC = 16;                   // doubles of the feature axis per stage
 constexpr int kSyrkRS = kSyrkKC + 8;          // padded row stride: == 8 mod 16
 constexpr int kSyrkStages = 4;
 constexpr int kSyrkThreads = 256;
 constexpr size_t kSyrkStageDoubles = 2 * (size_t)kSyrkTile * kSyrkRS;
-constexpr size_t kSyrkSmem = kSyrkStages * kSyrkStageDoubles * sizeof(double);   // 160 KB
+constexpr size_t kSyrkSmem = kSyrkStages * kSyrkStageDoubles * sizeof(double);   // 192 KB
+static_assert(kSyrkSmem <= 227 * 1024, "SYRK pipeline does not fit in shared memory");
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
 {
@@ -75,14 +76,15 @@ syrk_tile_kernel(const double* __restrict__ X, long ldx, int T, int dpad, int nt
     const int lr = lane & 3, lc = lane >> 2;
     const int wm = warp >> 2, wn = warp & 3;         // warp tile origin: rows wm*64, columns wn*32
 
-    // loader mapping: 16 threads cover the 256 bytes of a row segment; 16 rows per pass
-    const int lrow = tid >> 4, lchunk = tid & 15;
-    const double* srcA[8];
-    const double* srcB[8];
+    // loader mapping: 8 threads cover the 128 bytes of a row segment; 32 rows per pass
+    constexpr int kPasses = 4;
+    const int lrow = tid >> 3, lchunk = tid & 7;
+    const double* srcA[kPasses];
+    const double* srcB[kPasses];
 #pragma unroll
-    for (int p = 0; p < 8; ++p) {
-        int ra = ti * kSyrkTile + p * 16 + lrow;
-        int rb = tj * kSyrkTile + p * 16 + lrow;
+    for (int p = 0; p < kPasses; ++p) {
+        int ra = ti * kSyrkTile + p * 32 + lrow;
+        int rb = tj * kSyrkTile + p * 32 + lrow;
         if (ra >= T) ra = T - 1;                      // clamped rows: results are discarded
         if (rb >= T) rb = T - 1;
         srcA[p] = X + (long)ra * ldx + (long)c_begin * kSyrkKC + lchunk * 2;
@@ -93,9 +95,9 @@ syrk_tile_kernel(const double* __restrict__ X, long ldx, int T, int dpad, int nt
         double* b = a + (size_t)kSyrkTile * kSyrkRS;
         const long off = (long)chunk * kSyrkKC;
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
-            cp_async16(a + (p * 16 + lrow) * kSyrkRS + lchunk * 2, srcA[p] + off);
-            if (!diag) cp_async16(b + (p * 16 + lrow) * kSyrkRS + lchunk * 2, srcB[p] + off);
+        for (int p = 0; p < kPasses; ++p) {
+            cp_async16(a + (p * 32 + lrow) * kSyrkRS + lchunk * 2, srcA[p] + off);
+            if (!diag) cp_async16(b + (p * 32 + lrow) * kSyrkRS + lchunk * 2, srcB[p] + off);
         }
     };
 
@@ -201,14 +203,14 @@ static int syrk_sm_count()
 }
 
 // number of feature splits: the smallest split count (<= 16) whose (tiles x splits) wastes the
-// fewest SM slots in its last wave; at least 8 chunks of 32 features per split
+// fewest SM slots in its last wave; at least 16 chunks of 16 features per split
 static int syrk_splits(int ntri, int nchunks)
 {
     const int nsm = syrk_sm_count();
     int best = 1;
     double best_eff = 0.0;
     for (int s = 1; s <= 16; ++s) {
-        if (s > 1 && nchunks / s < 8) break;
+        if (s > 1 && nchunks / s < 16) break;
         const long items = (long)ntri * s;
         const long waves = (items + nsm - 1) / nsm;
         const double eff = (double)items / (double)(waves * nsm);

@@ -110,14 +110,13 @@ def test_sharded_engines_nccl_world2(tmp_path):
 def test_peer_collectives_world2(tmp_path):
     """Peer-memory collectives (include/cdr_b200.h, cdr_peer_*) on two GPUs: stand-alone
     all-reduce / all-gather against NCCL, the fused reduce-over-samples + all-reduce against
-    the unfused pair (bit-identical for two ranks), and the sharded engines with
-    CDR_PEER_COLLECTIVES=1 against the same engines over NCCL.  Opt-in while the path is
-    opt-in: set CDR_TEST_PEER=1."""
+    the unfused pair (bit-identical for two ranks), and the sharded engines over peer memory
+    (the default; at streaming shapes the whole iteration runs behind cdr_gpnh_iterate_enqueue /
+    cdr_aa_iterate_enqueue with the exchanges inside the kernels) against the same engines
+    over NCCL (CDR_PEER_COLLECTIVES=0)."""
     torch = pytest.importorskip('torch')
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip('needs two GPUs')
-    if os.environ.get('CDR_TEST_PEER', '0') != '1':
-        pytest.skip('peer collectives are opt-in (CDR_TEST_PEER=1)')
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     from _dist_worker import problem
     out = str(tmp_path / 'peer.npz')

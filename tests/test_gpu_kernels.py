@@ -232,6 +232,24 @@ def test_gram_frobenius_residual():
     close(float(out.item()), np.linalg.norm(X - Z.dot(A)) ** 2, rtol=1e-13)
 
 
+@pytest.mark.parametrize('T,d', [(1, 5), (37, 70), (128, 64), (129, 333), (257, 1000), (700, 4180)])
+def test_syrk_gram_matches_numpy_and_the_slab_path(T, d):
+    """K = X X' (archetypal_analysis.py:1032) by the SYRK kernel: symmetric to the bit, equal
+    to NumPy and to the round-1 slab path to rounding, deterministic; tile edges (T not a
+    multiple of 128, d not a multiple of 32) included."""
+    rs = np.random.RandomState(T + d)
+    X = rs.standard_normal((T, d))
+    Xd = be.to_device_padded(X)
+    K = be.gram(Xd, T, d)
+    Kh = be.to_host(K, T, T)
+    assert np.array_equal(Kh, Kh.T)
+    scale = np.abs(X.dot(X.T)).max()
+    close(Kh, X.dot(X.T), rtol=0, atol=1e-13 * scale * np.sqrt(d))
+    close(Kh, be.to_host(be.gram_slabs(Xd, T, d), T, T), rtol=0, atol=1e-13 * scale * np.sqrt(d))
+    assert torch.equal(K, be.gram(Xd, T, d))
+    assert float(K[:, T:].abs().sum()) == 0.0
+
+
 @pytest.mark.parametrize('k,n', [(1, 10), (5, 33), (8, 1620), (20, 700), (64, 5000)])
 def test_small_gram(k, n):
     rs = np.random.RandomState(k * n)

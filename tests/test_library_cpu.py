@@ -48,12 +48,14 @@ def test_struct_layouts_match_the_header(tmp_path):
     from convex_dim_red import _backend as be
     src = tmp_path / 'sizes.c'
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "cdr_b200.h"\n'
-                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %d %u\\n", '
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %d %u %zu %zu %zu %zu\\n", '
                    'sizeof(cdr_spg_params),'
                    'sizeof(cdr_loop_state), sizeof(cdr_small_gram_desc), sizeof(cdr_aa_buffers),'
                    'offsetof(cdr_loop_state, tolerance), offsetof(cdr_aa_buffers, grad_scale),'
                    'sizeof(cdr_peer_group), offsetof(cdr_peer_group, inbox_offset),'
-                   'CDR_MAX_PEERS, CDR_PEER_HEADER_BYTES);'
+                   'CDR_MAX_PEERS, CDR_PEER_HEADER_BYTES, sizeof(cdr_gpnh_problem),'
+                   'sizeof(cdr_aa_problem), offsetof(cdr_gpnh_problem, peers),'
+                   'offsetof(cdr_aa_problem, peers));'
                    'return 0;}\n')
     exe = tmp_path / 'sizes'
     subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
@@ -62,7 +64,8 @@ def test_struct_layouts_match_the_header(tmp_path):
             ctypes.sizeof(be.SmallGramDesc), ctypes.sizeof(be.AaBuffers),
             be.LoopState.tolerance.offset, be.AaBuffers.grad_scale.offset,
             ctypes.sizeof(be.PeerGroupStruct), be.PeerGroupStruct.inbox_offset.offset,
-            be.MAX_PEERS, be.PEER_HEADER_BYTES]
+            be.MAX_PEERS, be.PEER_HEADER_BYTES, ctypes.sizeof(be.GpnhProblem),
+            ctypes.sizeof(be.AaProblem), be.GpnhProblem.peers.offset, be.AaProblem.peers.offset]
     assert got == want
 
 
@@ -73,7 +76,7 @@ def test_peer_collective_host_logic(lib):
     inbox, data, total = _peer.region_layout(8, 3 * 1000 + 5, 8 * 44000 * 8)
     assert inbox == be.PEER_HEADER_BYTES and data == inbox + 8 * _peer.round_up(8 * 44000 * 8)
     assert total == data + _peer.round_up(3005) and total % _peer.ALIGN == 0
-    assert not _peer.peer_collectives_enabled() or os.environ.get('CDR_PEER_COLLECTIVES') == '1'
+    assert _peer.peer_collectives_enabled() == (os.environ.get('CDR_PEER_COLLECTIVES', '1') != '0')
 
     g = be.PeerGroupStruct()
     g.world, g.rank, g.region_bytes = 2, 0, 16 << 20

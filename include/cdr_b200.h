@@ -108,6 +108,10 @@ int cdr_debug_stream_plan(int T, int d, int k, int with_epilogue, int* out);
  * flops = 2 * 256 * 8 * iters * 8 * blocks.  The result is the roofline denominator of the
  * tensor-bound shapes (Gram, k = 64), which MEASURED_PEAKS.json does not carry. */
 int cdr_debug_dmma_probe(double* out, int blocks, int iters, cdr_stream_t stream);
+/* debugging aids: CDR_DEBUG_SYNC=1 synchronises after every launch and reports the first
+ * failing one; CDR_TIME_LAUNCHES=1 records an event after every (eager, default-stream) launch
+ * and this call prints the time between consecutive events per launch site. */
+int cdr_debug_timing_report(int skip);
 
 /* ------------------------------------------------------------------ simplex
  * Euclidean projection of each row / column of A onto the probability simplex.
@@ -320,8 +324,10 @@ typedef struct cdr_peer_group {
     int rank;
     void* region[CDR_MAX_PEERS]; /* region[rank] is the local allocation */
     size_t region_bytes;
-    size_t inbox_offset;         /* world slots of inbox_slot_bytes: push area of the fused kernel */
-    size_t inbox_slot_bytes;
+    size_t inbox_offset;         /* world + 1 slots of inbox_slot_bytes: push area of the fused
+                                    kernel (one slot per sending rank, one for the results) */
+    size_t inbox_slot_bytes;     /* >= 4 x the bytes of the exchanged k x ldo matrix: two
+                                    alternating sets of 16-byte tagged words per double */
 } cdr_peer_group;
 
 int cdr_peer_region_alloc(size_t bytes, void** region);  /* cudaMalloc + clear */
@@ -347,9 +353,10 @@ int cdr_peer_allgather_columns(const cdr_peer_group* group, const double* src, l
 
 /* cdr_reduce_samples fused with the sum over ranks: out (k x ldo, at out_offset of every
  * region) = sum_r E (L_r X_r).  Each CTA pushes the tile of its feature strip straight from
- * the epilogue into the inbox of the strip's owner rank, which sums the world tiles in rank
- * order and pushes the result into `out` of every rank; the kernel ends when the local `out`
- * is complete.  T_min = the smallest local T of any rank (keeps the kernel choice identical
+ * the epilogue into the inbox of the strip's owner rank -- every double as two 8-byte words
+ * carrying 32 data bits and a 32-bit epoch tag, so that no fence and no flag message is
+ * needed --, the owner sums the world tiles in rank order as they arrive and pushes the
+ * result, tagged, to every rank; the kernel ends when the local `out` is complete.  T_min = the smallest local T of any rank (keeps the kernel choice identical
  * on all ranks).  Returns CDR_ERR_NOT_APPLICABLE for shapes the strip kernel does not cover
  * (then: cdr_reduce_samples followed by cdr_peer_allreduce). */
 int cdr_reduce_samples_allreduce(const cdr_peer_group* group, const double* Lp, long sLi,

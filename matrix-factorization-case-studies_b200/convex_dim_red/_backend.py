@@ -126,6 +126,7 @@ SIGNATURES = {
     'cdr_launch_count': (ctypes.c_ulonglong, []),
     'cdr_debug_stream_plan': (_i, [_i, _i, _i, _i, ctypes.POINTER(ctypes.c_int)]),
     'cdr_debug_dmma_probe': (_i, [_vp, _i, _i, _vp]),
+    'cdr_debug_timing_report': (_i, [_i]),
     'cdr_simplex_project_rows': (_i, [_vp, _vp, _i, _i, _l, _l, _vp, _vp]),
     'cdr_simplex_project_columns': (_i, [_vp, _vp, _i, _i, _l, _l, _vp, _vp]),
     'cdr_quad_simplex_spg_batched': (_i, [_vp, _vp, _vp, _l, _l, _vp, _i, _i,

@@ -57,7 +57,8 @@ class Comm:
             return None
         count = lambda shape: int(np.prod(shape))
         data_bytes = sum(_peer.round_up(count(s) * 8 + 8) for s in shapes)
-        slot_bytes = count(inbox_shape) * 8
+        # the fused exchange keeps two alternating sets of 16-byte tagged words per double
+        slot_bytes = 4 * count(inbox_shape) * 8
         if self.peer is not None and not self.peer.fits(data_bytes, slot_bytes):
             self.peer.close()
             self.peer = None

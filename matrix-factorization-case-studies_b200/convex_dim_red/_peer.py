@@ -32,10 +32,11 @@ def round_up(n, m=ALIGN):
 
 
 def region_layout(world, data_bytes, inbox_slot_bytes):
-    """(inbox offset, data offset, total bytes) of a region: header | world inbox slots | data."""
+    """(inbox offset, data offset, total bytes) of a region:
+    header | world inbox slots + one result slot | data."""
     slot = round_up(inbox_slot_bytes)
     inbox_offset = be.PEER_HEADER_BYTES
-    data_offset = inbox_offset + world * slot
+    data_offset = inbox_offset + (world + 1) * slot
     return inbox_offset, data_offset, data_offset + round_up(data_bytes)
 
 
@@ -170,7 +171,8 @@ class PeerGroup:
         be.check(be.library().cdr_peer_error(ctypes.byref(self.struct), ctypes.byref(err),
                                              be.stream_ptr()), 'cdr_peer_error')
         if err.value:
-            what = {1: 'start barrier', 2: 'finish barrier', 3: 'strip tiles', 4: 'strip sums'}
+            what = {1: 'start barrier', 2: 'finish barrier', 3: 'strip tiles', 4: 'strip sums',
+                    5: 'statistics of a peer'}
             raise be.BackendError('peer collective timed out waiting for %s (rank %d)'
                                   % (what.get(err.value, err.value), self.comm.rank))
 

@@ -29,8 +29,21 @@ static inline bool cdr_debug_sync()
     }
     return v == 1;
 }
+// CDR_TIME_LAUNCHES=1 (debugging aid, eager launches only): an event after every launch;
+// cdr_debug_timing_report() prints the time between consecutive events per launch site.
+void cdr_debug_note_launch(const char* file, int line);
+static inline bool cdr_debug_timing()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("CDR_TIME_LAUNCHES");
+        v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
 #define CDR_RETURN_IF_LAUNCH_FAILED()                                                       \
     do {                                                                                    \
+        if (cdr_debug_timing()) cdr_debug_note_launch(__FILE__, __LINE__);                  \
         cudaError_t e__ = cudaGetLastError();                                               \
         if (e__ == cudaSuccess && cdr_debug_sync()) e__ = cudaDeviceSynchronize();          \
         if (e__ != cudaSuccess) {                                                           \
@@ -186,6 +199,17 @@ int run_reduce_features_tma(const double* M, long ldm, const double* X, long ldx
 bool features_strip_geometry(int T, int d, int k, int* TC, int* nstrips);
 size_t reduce_features_tma_workspace_bytes(int T, int d, int k);
 void tma_stream_plan(int T, int d, int k, int with_epilogue, int* out);
+// stream_gemm64.cu: GEMM-shaped kernels for 16 < k <= 64 (tensor-bound shapes); return
+// CDR_TMA_NOT_APPLICABLE for shapes they do not take
+bool gemm64_applicable(int T, int d, int k);
+size_t features64_workspace_bytes(int T, int d, int k);
+size_t samples64_workspace_bytes(int T, int d, int k);
+int run_reduce_features64(const double* M, long ldm, const double* X, long ldx, int T, int d, int k,
+                          double* out, long ldo, void* workspace, size_t workspace_bytes,
+                          const cdr_flags* flags, cudaStream_t stream);
+int run_reduce_samples64(const double* Lp, long sLi, long sLt, const double* X, long ldx, int T, int d,
+                         int k, const double* E, double* out, long ldo, void* workspace,
+                         size_t workspace_bytes, const cdr_flags* flags, cudaStream_t stream);
 int run_reduce_samples_exchange(const cdr_peer_group& g, size_t out_offset, const double* Lp,
                                 long sLi, long sLt, const double* X, long ldx, int T, int T_min,
                                 int d, int k, const double* E, long ldo, const cdr_flags* flags,

@@ -224,11 +224,13 @@ extern "C" int cdr_reduce_samples_allreduce(const cdr_peer_group* group, const d
     const size_t bytes = (size_t)k * ldo * sizeof(double);
     CDR_CHECK_ARG(out_offset % 16 == 0 && out_offset >= CDR_PEER_HEADER_BYTES &&
                   out_offset + bytes <= group->region_bytes);
-    CDR_CHECK_ARG(group->inbox_offset % 16 == 0 && group->inbox_slot_bytes % 16 == 0 &&
+    // world inbox slots + one result slot; a slot holds two alternating sets of tagged words
+    // (16 bytes per double): 4 x the bytes of the k x ldo matrix
+    CDR_CHECK_ARG(group->inbox_offset % 16 == 0 && group->inbox_slot_bytes % 32 == 0 &&
                   group->inbox_offset >= CDR_PEER_HEADER_BYTES &&
-                  group->inbox_offset + (size_t)group->world * group->inbox_slot_bytes <=
+                  group->inbox_offset + (size_t)(group->world + 1) * group->inbox_slot_bytes <=
                       group->region_bytes);
-    if (bytes > group->inbox_slot_bytes) return CDR_ERR_NOT_APPLICABLE;
+    if (4 * bytes > group->inbox_slot_bytes) return CDR_ERR_NOT_APPLICABLE;
     return run_reduce_samples_exchange(*group, out_offset, Lp, sLi, sLt, X, ldx, T, T_min, d, k, E,
                                        ldo, flags, (cudaStream_t)stream);
 }

@@ -44,8 +44,9 @@ struct PeerHeader {
     // one-shot exchanges of small vectors by the tails of the fused iteration kernels
     // (cta_allreduce_small): two slot sets used alternately, one slot and one flag per peer
     unsigned long long small_epoch;
-    unsigned long long small_flag[2][CDR_MAX_PEERS];
-    double small_slot[2][CDR_MAX_PEERS][CDR_PEER_SMALL_MAX];
+    // per double two 8-byte words {32 data bits | 32-bit epoch tag}: data and flag travel in
+    // the same store, so no fence and no separate flag round trip is needed
+    unsigned long long small_ll[2][CDR_MAX_PEERS][2 * CDR_PEER_SMALL_MAX];
 };
 static_assert(sizeof(PeerHeader) <= CDR_PEER_HEADER_BYTES, "peer header does not fit");
 
@@ -88,6 +89,18 @@ __device__ __forceinline__ double ld_sys_d(const double* p)
 
 constexpr long long kWaitCycles = 4000000000LL;      // ~2 s at 1.9 GHz
 
+// "LL" words: a double travels as two 8-byte words, each carrying 32 data bits and a 32-bit
+// tag (the epoch of the exchange).  Data and flag arrive in the same store, so the writer
+// needs no fence and no separate flag message, and the reader polls the words themselves.
+__device__ __forceinline__ void st_ll(unsigned long long* dst, double v, unsigned long long tag)
+{
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long lo = (bits & 0xffffffffull) | tag;
+    const unsigned long long hi = (bits >> 32) | tag;
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};\n" ::"l"(dst), "l"(lo), "l"(hi)
+                 : "memory");
+}
+
 // Spin until *flag >= epoch.  On timeout records `what` in the local header and returns.
 __device__ __forceinline__ void wait_flag(const unsigned long long* flag, unsigned long long epoch,
                                           PeerHeader* mine, int what)
@@ -103,6 +116,32 @@ __device__ __forceinline__ void wait_flag(const unsigned long long* flag, unsign
             return;
         }
     }
+}
+
+// Polls a word pair until both carry `tag` (bounded like wait_flag) and returns the double.
+__device__ __forceinline__ double ld_ll(const unsigned long long* src, unsigned long long tag,
+                                        PeerHeader* mine, int what)
+{
+    unsigned long long lo, hi;
+    long long t0 = 0;
+    bool timing = false;
+    while (true) {
+        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];\n"
+                     : "=l"(lo), "=l"(hi)
+                     : "l"(src)
+                     : "memory");
+        if ((lo & 0xffffffff00000000ull) == tag && (hi & 0xffffffff00000000ull) == tag) break;
+        if (!timing) {
+            t0 = clock64();
+            timing = true;
+        }
+        if (*((volatile int*)&mine->error) != 0) break;
+        if (clock64() - t0 > kWaitCycles) {
+            atomicExch(&mine->error, what);
+            break;
+        }
+    }
+    return __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
 }
 
 // Barrier over CTA `blockIdx.x` of all ranks (every thread of the CTA must call it).
@@ -129,35 +168,64 @@ __device__ __forceinline__ void cta_barrier_all_ranks(const cdr_peer_group& g,
 
 // In-place sum over ranks of the n <= CDR_PEER_SMALL_MAX doubles vals[0..n) (shared or global
 // memory of the calling CTA), executed by ONE CTA per rank -- the last CTA of a fused kernel,
-// after it has reduced its own rank's partials.  One shot: every rank pushes its vector into
-// slot[rank] of every peer, raises a flag there, waits for the flags of all peers and sums the
-// slots in rank order (so every rank gets the same bits).  Doubles as a barrier between the
-// ranks (n = 0): data pushed to peer memory by the calling kernel before this call -- by any
-// of its CTAs, provided they fenced at system scope before the caller learnt it is last --
-// has arrived when it returns.  Two slot sets alternate: a rank can be at most one exchange
-// ahead of its peers (it cannot finish exchange e + 1 before every peer has entered it, i.e.
-// has finished reading exchange e).  All threads of the CTA must call this.
+// after it has reduced its own rank's partials.  One shot, low latency: every rank writes its
+// vector into slot[rank] of every peer as 8-byte words that carry 32 data bits and a 32-bit
+// epoch tag (the "LL" scheme: the flag travels inside the store, so neither a fence nor a
+// separate flag message is needed; one NVLink one-way latency in all), then polls the slots
+// of all peers in its own region and sums them in rank order (every rank gets the same bits).
+// Doubles as a barrier between the ranks (vals = nullptr): bulk data pushed to peer memory
+// by the calling kernel before this call has arrived when it returns, PROVIDED every CTA
+// that pushed fenced at system scope before the caller learnt it is the last CTA (the
+// pushes are then performed before the tagged words are even sent).  Two slot sets alternate:
+// a rank can be at most one exchange ahead of its peers (it cannot finish exchange e + 1
+// before every peer has entered it, i.e. has finished reading exchange e).  All threads of
+// the CTA must call this.
 __device__ __forceinline__ void cta_allreduce_small(const cdr_peer_group& g, double* vals, int n)
 {
     PeerHeader* mine = header_of(g, g.rank);
     const unsigned long long epoch = *((volatile unsigned long long*)&mine->small_epoch) + 1;
     const int set = (int)(epoch & 1ull);
+    const unsigned long long tag = (epoch & 0xffffffffull) << 32;
+    const int n_eff = (vals == nullptr || n < 1) ? 1 : n;         // a barrier sends one word pair
     for (int r = 0; r < g.world; ++r) {
-        double* dst = header_of(g, r)->small_slot[set][g.rank];
-        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = vals[i];
+        unsigned long long* dst = header_of(g, r)->small_ll[set][g.rank];
+        for (int i = threadIdx.x; i < n_eff; i += blockDim.x) {
+            const unsigned long long bits =
+                (vals == nullptr) ? 0ull : (unsigned long long)__double_as_longlong(vals[i]);
+            const unsigned long long lo = (bits & 0xffffffffull) | tag;
+            const unsigned long long hi = (bits >> 32) | tag;
+            asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};\n" ::"l"(dst + 2 * i), "l"(lo),
+                         "l"(hi)
+                         : "memory");
+        }
     }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < g.world) {
-        const int p = threadIdx.x;
-        st_release_sys(&header_of(g, p)->small_flag[set][g.rank], epoch);
-        wait_flag(&mine->small_flag[set][p], epoch, mine, kWaitSmall);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        double s = ld_sys_d(&mine->small_slot[set][0][i]);
-        for (int r = 1; r < g.world; ++r) s += ld_sys_d(&mine->small_slot[set][r][i]);
-        vals[i] = s;
+    for (int i = threadIdx.x; i < n_eff; i += blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < g.world; ++r) {
+            const unsigned long long* src = mine->small_ll[set][r] + 2 * i;
+            unsigned long long lo, hi;
+            long long t0 = 0;
+            bool timing = false;
+            while (true) {
+                asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];\n"
+                             : "=l"(lo), "=l"(hi)
+                             : "l"(src)
+                             : "memory");
+                if ((lo & 0xffffffff00000000ull) == tag && (hi & 0xffffffff00000000ull) == tag) break;
+                if (!timing) {
+                    t0 = clock64();
+                    timing = true;
+                }
+                if (*((volatile int*)&mine->error) != 0) break;
+                if (clock64() - t0 > kWaitCycles) {
+                    atomicExch(&mine->error, kWaitSmall);
+                    break;
+                }
+            }
+            const double v = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+            s = (r == 0) ? v : s + v;
+        }
+        if (vals != nullptr && i < n) vals[i] = s;
     }
     __syncthreads();
     if (threadIdx.x == 0) *((volatile unsigned long long*)&mine->small_epoch) = epoch;

@@ -445,7 +445,9 @@ extern "C" size_t cdr_reduce_samples_workspace_bytes(int T, int d, int k)
 {
     const int dpad = (d + 31) / 32 * 32;
     const int ns = samples_nsplit(T, dpad);
-    return (size_t)ns * k * dpad * sizeof(double);
+    const size_t direct = (size_t)ns * k * dpad * sizeof(double);
+    const size_t gemm = samples64_workspace_bytes(T, d, k);
+    return direct > gemm ? direct : gemm;
 }
 
 extern "C" int cdr_reduce_samples(const double* Lp, long sLi, long sLt, const double* X, long ldx,
@@ -458,6 +460,12 @@ extern "C" int cdr_reduce_samples(const double* Lp, long sLi, long sLt, const do
     const int dpad = (d + 31) / 32 * 32;
     CDR_CHECK_ARG(ldx >= dpad && ldo >= dpad && ldx % 2 == 0 && ldo % 2 == 0);
     cudaStream_t s = (cudaStream_t)stream;
+    {
+        // 16 < k <= 64: the tensor-bound GEMM-shaped kernel
+        const int rc = run_reduce_samples64(Lp, sLi, sLt, X, ldx, T, d, k, E, out, ldo, workspace,
+                                            workspace_bytes, flags, s);
+        if (rc != CDR_TMA_NOT_APPLICABLE) return rc;
+    }
     {
         const int rc = run_reduce_samples_tma(Lp, sLi, sLt, X, ldx, T, d, k, E, out, ldo, flags, s);
         if (rc != CDR_TMA_NOT_APPLICABLE) return rc;
@@ -476,7 +484,9 @@ extern "C" size_t cdr_reduce_features_workspace_bytes(int T, int d, int k)
     const int kp = (k <= 8) ? 8 : (k <= 16) ? 16 : (k <= 24) ? 24 : (k <= 32) ? 32 : (k <= 48) ? 48 : 64;
     const size_t direct = (size_t)nchunk * T * kp * sizeof(double);
     const size_t piped = reduce_features_tma_workspace_bytes(T, d, k);
-    return direct > piped ? direct : piped;
+    const size_t gemm = features64_workspace_bytes(T, d, k);
+    const size_t a = direct > piped ? direct : piped;
+    return a > gemm ? a : gemm;
 }
 
 extern "C" int cdr_reduce_features(const double* M, long ldm, const double* X, long ldx, int T,
@@ -489,6 +499,12 @@ extern "C" int cdr_reduce_features(const double* M, long ldm, const double* X, l
     const int dpad = (d + 31) / 32 * 32;
     CDR_CHECK_ARG(ldx >= dpad && ldm >= dpad && ldo >= T && ldx % 2 == 0 && ldm % 2 == 0);
     cudaStream_t s = (cudaStream_t)stream;
+    {
+        // 16 < k <= 64: the tensor-bound GEMM-shaped kernel
+        const int rc = run_reduce_features64(M, ldm, X, ldx, T, d, k, out, ldo, workspace,
+                                             workspace_bytes, flags, s);
+        if (rc != CDR_TMA_NOT_APPLICABLE) return rc;
+    }
     {
         const int rc = run_reduce_features_tma(M, ldm, X, ldx, T, d, k, out, ldo, workspace,
                                                workspace_bytes, flags, s);

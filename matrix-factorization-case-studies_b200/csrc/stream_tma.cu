@@ -106,9 +106,14 @@ reduce_samples_tma_kernel(const double* __restrict__ Lp, long sLi, long sLt,
 
     // ---------------------------------- consumers
     const int lr = lane & 3, lc = lane >> 2;
-    unsigned long long epoch = 0;
-    if constexpr (kExchange)
+    unsigned long long epoch = 0, tag = 0;
+    size_t set_bytes = 0;                             // offset of this launch's set inside a slot
+    if constexpr (kExchange) {
         epoch = *((volatile unsigned long long*)&peer::header_of(xch.g, xch.g.rank)->fused_epoch) + 1;
+        tag = (epoch & 0xffffffffull) << 32;
+        set_bytes = (size_t)(epoch & 1ull) * (xch.g.inbox_slot_bytes / 2);
+    }
+    unsigned long long* ll_dst = nullptr;             // tagged words of the strip owner's inbox
     int it = 0;
     for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
         const int c0 = strip * TC;
@@ -117,9 +122,20 @@ reduce_samples_tma_kernel(const double* __restrict__ Lp, long sLi, long sLt,
         if constexpr (kExchange) {
             // this rank's slot in the inbox of the strip's owner takes the place of `out`
             const cdr_peer_group& g = xch.g;
-            out = reinterpret_cast<double*>(static_cast<unsigned char*>(g.region[strip % g.world]) +
-                                            g.inbox_offset + (size_t)g.rank * g.inbox_slot_bytes);
+            ll_dst = reinterpret_cast<unsigned long long*>(
+                static_cast<unsigned char*>(g.region[strip % g.world]) + g.inbox_offset +
+                (size_t)g.rank * g.inbox_slot_bytes + set_bytes);
         }
+        // one result element: a plain store, or -- sample-sharded -- two 8-byte words with 32
+        // data bits and the 32-bit epoch tag each, pushed to the owner (peer.cuh: no fence, no
+        // flag message; the reader polls the tags)
+        auto emit = [&](long el, double v) {
+            if constexpr (kExchange) {
+                peer::st_ll(ll_dst + 2 * el, v, tag);
+            } else {
+                out[el] = v;
+            }
+        };
 
         double acc[MAXU][KT][2][2];
 #pragma unroll
@@ -193,11 +209,19 @@ reduce_samples_tma_kernel(const double* __restrict__ Lp, long sLi, long sLt,
                 for (int mt = 0; mt < KT; ++mt) {
                     const int i = mt * 8 + lc;
                     if (i < k) {
-                        double* p = out + (long)i * ldo + fbase + 4 * lr;
-                        *reinterpret_cast<double2*>(p) =
-                            make_double2(acc[u][mt][0][0], acc[u][mt][1][0]);
-                        *reinterpret_cast<double2*>(p + 2) =
-                            make_double2(acc[u][mt][0][1], acc[u][mt][1][1]);
+                        const long el = (long)i * ldo + fbase + 4 * lr;
+                        if constexpr (kExchange) {
+                            emit(el, acc[u][mt][0][0]);
+                            emit(el + 1, acc[u][mt][1][0]);
+                            emit(el + 2, acc[u][mt][0][1]);
+                            emit(el + 3, acc[u][mt][1][1]);
+                        } else {
+                            double* p = out + el;
+                            *reinterpret_cast<double2*>(p) =
+                                make_double2(acc[u][mt][0][0], acc[u][mt][1][0]);
+                            *reinterpret_cast<double2*>(p + 2) =
+                                make_double2(acc[u][mt][0][1], acc[u][mt][1][1]);
+                        }
                     }
                 }
             } else {
@@ -219,66 +243,63 @@ reduce_samples_tma_kernel(const double* __restrict__ Lp, long sLi, long sLt,
                     double sacc = 0.0;
 #pragma unroll
                     for (int i = 0; i < KP; ++i) sacc = fma(Es[j * KP + i], col[i], sacc);
-                    out[(long)j * ldo + fbase + f] = sacc;
+                    emit((long)j * ldo + fbase + f, sacc);
                 }
                 __syncwarp();
             }
         }
 
         if constexpr (kExchange) {
+            // the owner of the strip sums the tiles of all ranks in rank order as they arrive
+            // (tagged words: no flag, no fence), stores the sum locally and pushes it, tagged,
+            // into the result buffer of every other rank
             const cdr_peer_group& g = xch.g;
-            const int owner = strip % g.world;
-            peer::PeerHeader* mine = peer::header_of(g, g.rank);
-            __threadfence_system();
-            samples_consumer_barrier();                       // the whole tile has been pushed
-            if (threadIdx.x == 0)
-                peer::st_release_sys(&peer::header_of(g, owner)->ready[strip][g.rank], epoch);
-            if (owner == g.rank) {
-                if ((int)threadIdx.x < g.world)
-                    peer::wait_flag(&mine->ready[strip][threadIdx.x], epoch, mine, peer::kWaitReady);
-                samples_consumer_barrier();                   // every rank's tile of this strip is here
-                const unsigned char* inbox =
-                    static_cast<const unsigned char*>(g.region[g.rank]) + g.inbox_offset;
-                const int w2 = w / 2;
-                for (int idx = threadIdx.x; idx < k * w2; idx += kConsumerWarps * 32) {
-                    const int i = idx / w2, c = (idx - i * w2) * 2;
-                    const size_t el = (size_t)i * ldo + c0 + c;
-                    double2 part[CDR_MAX_PEERS];
-#pragma unroll
-                    for (int r = 0; r < CDR_MAX_PEERS; ++r)
-                        if (r < g.world)
-                            part[r] = peer::ld_sys_d2(reinterpret_cast<const double*>(
-                                          inbox + (size_t)r * g.inbox_slot_bytes) + el);
-                    double2 sum = part[0];
-#pragma unroll
-                    for (int r = 1; r < CDR_MAX_PEERS; ++r)
-                        if (r < g.world) {
-                            sum.x += part[r].x;
-                            sum.y += part[r].y;
-                        }
-#pragma unroll
-                    for (int r = 0; r < CDR_MAX_PEERS; ++r)
-                        if (r < g.world)
-                            *reinterpret_cast<double2*>(
-                                reinterpret_cast<double*>(static_cast<unsigned char*>(g.region[r]) +
-                                                          xch.out_offset) + el) = sum;
+            if (strip % g.world == g.rank) {
+                peer::PeerHeader* mine = peer::header_of(g, g.rank);
+                unsigned char* base = static_cast<unsigned char*>(g.region[g.rank]) + g.inbox_offset;
+                double* local_out = reinterpret_cast<double*>(
+                    static_cast<unsigned char*>(g.region[g.rank]) + xch.out_offset);
+                for (int idx = threadIdx.x; idx < k * w; idx += kConsumerWarps * 32) {
+                    const int i = idx / w, c = idx - i * w;
+                    const long el = (long)i * ldo + c0 + c;
+                    double sum = 0.0;
+                    for (int r = 0; r < g.world; ++r) {
+                        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(
+                            base + (size_t)r * g.inbox_slot_bytes + set_bytes) + 2 * el;
+                        const double v = peer::ld_ll(src, tag, mine, peer::kWaitReady);
+                        sum = (r == 0) ? v : sum + v;
+                    }
+                    local_out[el] = sum;
+                    for (int r = 0; r < g.world; ++r)
+                        if (r != g.rank)
+                            peer::st_ll(reinterpret_cast<unsigned long long*>(
+                                            static_cast<unsigned char*>(g.region[r]) + g.inbox_offset +
+                                            (size_t)g.world * g.inbox_slot_bytes + set_bytes) + 2 * el,
+                                        sum, tag);
                 }
-                __threadfence_system();
-                samples_consumer_barrier();                   // the sum has been pushed to every rank
-                if ((int)threadIdx.x < g.world)
-                    peer::st_release_sys(&peer::header_of(g, threadIdx.x)->done[strip], epoch);
             }
         }
     }
 
     if constexpr (kExchange) {
-        // the local `out` is complete once the owners of all strips of this CTA said so; this
-        // also keeps a fast rank from pushing the next launch's tiles into an inbox slot whose
-        // owner has not consumed the current ones
-        peer::PeerHeader* mine = peer::header_of(xch.g, xch.g.rank);
-        for (int strip = blockIdx.x + (int)threadIdx.x * (int)gridDim.x; strip < nstrips;
-             strip += kConsumerWarps * 32 * (int)gridDim.x)
-            peer::wait_flag(&mine->done[strip], epoch, mine, peer::kWaitDone);
+        // the sums of the strips other ranks own arrive, tagged, in this rank's result buffer
+        const cdr_peer_group& g = xch.g;
+        peer::PeerHeader* mine = peer::header_of(g, g.rank);
+        const unsigned long long* res = reinterpret_cast<const unsigned long long*>(
+            static_cast<unsigned char*>(g.region[g.rank]) + g.inbox_offset +
+            (size_t)g.world * g.inbox_slot_bytes + set_bytes);
+        double* local_out = reinterpret_cast<double*>(static_cast<unsigned char*>(g.region[g.rank]) +
+                                                      xch.out_offset);
+        for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+            if (strip % g.world == g.rank) continue;
+            const int c0 = strip * TC;
+            const int w = min(TC, dpad - c0);
+            for (int idx = threadIdx.x; idx < k * w; idx += kConsumerWarps * 32) {
+                const int i = idx / w, c = idx - i * w;
+                const long el = (long)i * ldo + c0 + c;
+                local_out[el] = peer::ld_ll(res + 2 * el, tag, mine, peer::kWaitDone);
+            }
+        }
         samples_consumer_barrier();
         if (threadIdx.x == 0) {
             // the last CTA to leave publishes the epoch for the next launch (all CTAs of this

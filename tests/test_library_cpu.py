@@ -74,7 +74,8 @@ def test_peer_collective_host_logic(lib):
     without a GPU (no kernel is launched: every call below is rejected on its arguments)."""
     from convex_dim_red import _backend as be, _peer
     inbox, data, total = _peer.region_layout(8, 3 * 1000 + 5, 8 * 44000 * 8)
-    assert inbox == be.PEER_HEADER_BYTES and data == inbox + 8 * _peer.round_up(8 * 44000 * 8)
+    # header | world inbox slots + one result slot | data
+    assert inbox == be.PEER_HEADER_BYTES and data == inbox + 9 * _peer.round_up(8 * 44000 * 8)
     assert total == data + _peer.round_up(3005) and total % _peer.ALIGN == 0
     assert _peer.peer_collectives_enabled() == (os.environ.get('CDR_PEER_COLLECTIVES', '1') != '0')
 

@@ -80,6 +80,8 @@ def parse_args():
                     help='skip the 18 000 x 44 000, k = 64 stress shape (BASELINE configs[4])')
     ap.add_argument('--no-strong', action='store_true',
                     help='N > 1: skip the strong-scaling (fixed total size) measurements')
+    ap.add_argument('--no-kmeans', action='store_true',
+                    help='skip the k-means block (BASELINE configs[2])')
     ap.add_argument('--no-numba', action='store_true',
                     help='reference arm: skip timing the real (Numba) reference from baseline/_ref')
     return ap.parse_args()
@@ -523,6 +525,73 @@ def strong_scaling(args, rank, world, comm):
     return out
 
 
+def kmeans_block(args, hbm_peak, peak_src):
+    """BASELINE.json configs[2]: k-means k = 8 with FurthestSum initialisation on a synthetic
+    JRA-55 hgt500-shaped field (700 months x 41 800 grid points), scikit-learn's KMeans with the
+    same initial centres beside it (the third-party code the drivers call,
+    bin/run_hadisst_kmeans.py:128-131)."""
+    import torch
+    from sklearn.cluster import KMeans as SkKMeans
+    from convex_dim_red.datasets import synthetic_field
+    from convex_dim_red.kmeans import furthest_sum_centres, kmeans_lloyd
+    T, d, k = 700, 41800, 8
+    X = synthetic_field(T, d, seed=5)
+    start = int(np.random.RandomState(0).randint(T))
+    picks = furthest_sum_centres(X, k, start, 10)
+    t0 = time.perf_counter()
+    picks = furthest_sum_centres(X, k, start, 10)
+    torch.cuda.synchronize()
+    t_init = time.perf_counter() - t0
+    init = X[picks].copy()
+    kmeans_lloyd(X, init, tol=1e-4, max_iter=10000)               # warm-up
+    fits = []
+    for _ in range(3):
+        stats = {}
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        labels, centres, inertia, n_iter = kmeans_lloyd(X, init, tol=1e-4, max_iter=10000,
+                                                        stats=stats)
+        torch.cuda.synchronize()
+        fits.append((time.perf_counter() - t0, stats))
+    fit_s, stats = sorted(fits, key=lambda f: f[0])[1]
+    # steady-state Lloyd iterations (the synthetic field converges in a handful, so the
+    # iteration throughput is timed on 200 re-armed iterations from the initial centres)
+    ms_iter = kmeans_lloyd(X, init, tol=1e-4, max_iter=10000, _time_iterations=200)
+    pass_bytes = 8.0 * T * d
+    t0 = time.perf_counter()
+    sk = SkKMeans(n_clusters=k, init=init, n_init=1, algorithm='lloyd', tol=1e-4,
+                  max_iter=10000).fit(X)
+    t_sk = time.perf_counter() - t0
+    return {
+        'workload': 'k-means k=%d, FurthestSum init, %d x %d fp64 (BASELINE.json configs[2])' % (k, T, d),
+        'metric': 'kmeans_lloyd_iterations_per_sec_jra55', 'value': 1e3 / ms_iter,
+        'unit': 'iterations/s', 'ms_per_lloyd_iteration': ms_iter, 'n_iter': int(n_iter),
+        'device_loop': stats['device_loop'], 'fit_loop_ms': stats['loop_ms'],
+        'timed': '200 graph-replayed Lloyd iterations (5 kernels each), CUDA events',
+        'roofline': {'bound': 'hbm', 'kernel': 'the two streaming passes of a Lloyd iteration',
+                     'algorithmic_bytes_per_iteration': 2 * pass_bytes,
+                     'achieved': 2 * pass_bytes / (ms_iter * 1e-3) / 1e9, 'peak': hbm_peak,
+                     'unit': 'GB/s', 'frac': 2 * pass_bytes / (ms_iter * 1e-3) / 1e9 / hbm_peak,
+                     'peak_source': peak_src,
+                     'note': 'whole iteration (5 kernels incl. assignment and centre update); '
+                             'X (234 MB) is larger than the L2'},
+        'e2e': {'value': n_iter / fit_s, 'unit': 'iterations/s', 'fit_seconds': fit_s,
+                'h2d_bytes_per_step': X.nbytes / max(n_iter, 1),
+                'd2h_bytes_per_step': (labels.nbytes + centres.nbytes) / max(n_iter, 1),
+                'call': 'kmeans_lloyd(X, init): upload, centring, Lloyd iterations, labels and '
+                        'centres back; median of 3'},
+        'furthest_sum_init_seconds': t_init,
+        'cpu_baseline': {'value': sk.n_iter_ / t_sk, 'unit': 'iterations/s', 'kind': 'reference',
+                         'cores': os.cpu_count(), 'fit_seconds': t_sk, 'n_iter': int(sk.n_iter_),
+                         'sample': 'sklearn.cluster.KMeans(init=same centres, n_init=1, '
+                                   "algorithm='lloyd').fit(X), the whole fit"},
+        'parity': {'ok': bool(np.array_equal(labels, sk.labels_) and n_iter == sk.n_iter_),
+                   'labels_equal': bool(np.array_equal(labels, sk.labels_)),
+                   'n_iter': [int(n_iter), int(sk.n_iter_)],
+                   'inertia_rel_diff': abs(inertia - sk.inertia_) / sk.inertia_,
+                   'against': 'scikit-learn 1.9.0 KMeans, same initial centres'}}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -552,6 +621,7 @@ def run_b200(args):
     del Xd
     torch.cuda.empty_cache()
     strong = strong_scaling(args, rank, world, comm)
+    kmeans = kmeans_block(args, hbm_peak, peak_src) if (world == 1 and not args.no_kmeans) else None
 
     if rank == 0:
         head = blocks[workloads[0]]
@@ -561,6 +631,8 @@ def run_b200(args):
             head['gpu_launches'] += blocks['gpnh']['gpu_launches']
         if strong:
             head['strong_scaling'] = strong
+        if kmeans:
+            head['kmeans'] = kmeans
         print(json.dumps(head))
         sys.stdout.flush()
     if world > 1:

@@ -248,6 +248,12 @@ int cdr_aa_spg_update(const cdr_aa_buffers* b, const cdr_spg_params* p, int comp
  * end_of_iteration != 0 also applies the stopping rule and advances n_iter. */
 int cdr_aa_cost_check(const cdr_aa_buffers* b, int stage, int end_of_iteration,
                       cdr_stream_t stream);
+/* delta != 0: _update_kernel_aa_scale_factors (archetypal_analysis.py:220-258), the generic
+ * spg() on the k-vector b->alpha over the box [1 - delta, 1 + delta]^k, from b->ZtZ, b->CKCt,
+ * b->CKZ and state->trace_data; one warp, no host round trip.  params: defaults of spg()
+ * (spg.py:46-51). */
+int cdr_aa_scale_factors_step(const cdr_aa_buffers* b, const cdr_spg_params* p, double delta,
+                              cdr_stream_t stream);
 /* stand-alone df(C) -> b->G and f(C) -> *out (archetypal_analysis.py:261-301) */
 int cdr_aa_gradient(const cdr_aa_buffers* b, cdr_stream_t stream);
 int cdr_aa_dictionary_cost(const cdr_aa_buffers* b, double trace_data, double* out,
@@ -297,6 +303,48 @@ int cdr_column_moments(const double* X, long ldx, int T, int d, double* mean, do
                        cdr_stream_t stream);
 int cdr_center_columns(double* X, long ldx, int T, int d, const double* mean, double sign,
                        cdr_stream_t stream);
+
+/* One Lloyd iteration (scikit-learn `_kmeans_single_lloyd`, _kmeans.py:620-760) behind one
+ * call, stopping rule on the device: E step from the per-strip partials of centres . X', the
+ * per-cluster sums as one_hot' X, centre update and the tests "labels unchanged" / "total
+ * shift <= tol" / iteration limit by the last CTA (csrc/kmeans_iter.cu).  X is the centred
+ * data; `counts` is int[k]; the state block starts zeroed except max_iter and tol_abs.  An
+ * empty cluster stops the loop before the centre update with needs_relocation set (the caller
+ * relocates and finishes that iteration with the stand-alone calls above).  Returns
+ * CDR_ERR_NOT_APPLICABLE for shapes the strip kernels do not cover or k > 8. */
+typedef struct cdr_kmeans_state {
+    int done;              /* must stay first (the streaming kernels read it as cdr_flags) */
+    int n_iter;            /* completed Lloyd iterations */
+    int max_iter;
+    int strict;            /* labels did not change: strict convergence */
+    int needs_relocation;  /* an empty cluster was found */
+    int changed;           /* a label changed in the current E step */
+    unsigned int ticket;
+    int reserved_;
+    double tol_abs;        /* tol * mean per-feature variance (_kmeans.py:285-294) */
+    double shift_total;
+} cdr_kmeans_state;
+
+typedef struct cdr_kmeans_problem {
+    const double* X;       /* T x d centred data, leading dimension ldx */
+    long ldx;
+    int T, d, k;
+    double* centres;       /* k x ldx, updated in place */
+    int32_t* labels;       /* T, read (previous labels) and written */
+    double* onehot;        /* k x ldt */
+    long ldt;
+    double* sums;          /* k x ldx */
+    double* cnorm;         /* k */
+    double* shift;         /* k */
+    int* counts;           /* k */
+    cdr_kmeans_state* state;
+    void* workspace;       /* cdr_kmeans_workspace_bytes(T, d, k) */
+    size_t workspace_bytes;
+} cdr_kmeans_problem;
+
+size_t cdr_kmeans_workspace_bytes(int T, int d, int k);
+int cdr_kmeans_fused_applicable(int T, int d, int k);
+int cdr_kmeans_iterate_enqueue(const cdr_kmeans_problem* problem, cdr_stream_t stream);
 
 /* ------------------------------------------------------------------ peer-memory collectives
  * The exchange steps of the sample-sharded fit as kernels of this

@@ -94,6 +94,27 @@ class GpnhProblem(ctypes.Structure):
                 ('peers', ctypes.c_void_p), ('T_min', ctypes.c_int)]
 
 
+class KmeansState(ctypes.Structure):
+    """Mirror of ``cdr_kmeans_state``."""
+
+    _fields_ = [('done', ctypes.c_int), ('n_iter', ctypes.c_int), ('max_iter', ctypes.c_int),
+                ('strict', ctypes.c_int), ('needs_relocation', ctypes.c_int),
+                ('changed', ctypes.c_int), ('ticket', ctypes.c_uint), ('reserved_', ctypes.c_int),
+                ('tol_abs', ctypes.c_double), ('shift_total', ctypes.c_double)]
+
+
+class KmeansProblem(ctypes.Structure):
+    """Mirror of ``cdr_kmeans_problem``."""
+
+    _fields_ = [('X', ctypes.c_void_p), ('ldx', ctypes.c_long),
+                ('T', ctypes.c_int), ('d', ctypes.c_int), ('k', ctypes.c_int),
+                ('centres', ctypes.c_void_p), ('labels', ctypes.c_void_p),
+                ('onehot', ctypes.c_void_p), ('ldt', ctypes.c_long), ('sums', ctypes.c_void_p),
+                ('cnorm', ctypes.c_void_p), ('shift', ctypes.c_void_p), ('counts', ctypes.c_void_p),
+                ('state', ctypes.c_void_p), ('workspace', ctypes.c_void_p),
+                ('workspace_bytes', ctypes.c_size_t)]
+
+
 class AaProblem(ctypes.Structure):
     """Mirror of ``cdr_aa_problem``."""
 
@@ -156,6 +177,7 @@ SIGNATURES = {
     'cdr_aa_spg_direction': (_i, [ctypes.POINTER(AaBuffers), ctypes.POINTER(SpgParams), _vp]),
     'cdr_aa_spg_linesearch': (_i, [ctypes.POINTER(AaBuffers), ctypes.POINTER(SpgParams), _vp]),
     'cdr_aa_spg_update': (_i, [ctypes.POINTER(AaBuffers), ctypes.POINTER(SpgParams), _i, _vp]),
+    'cdr_aa_scale_factors_step': (_i, [ctypes.POINTER(AaBuffers), ctypes.POINTER(SpgParams), _d, _vp]),
     'cdr_aa_cost_check': (_i, [ctypes.POINTER(AaBuffers), _i, _i, _vp]),
     'cdr_gpnh_cost_check': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _i, _i, _vp]),
     'cdr_gpnh_workspace_bytes': (_sz, [_i, _i, _i]),
@@ -172,6 +194,9 @@ SIGNATURES = {
     'cdr_kmeans_labels': (_i, [_vp, _l, _vp, _i, _i, _vp, _vp, _l, _vp, _vp, _vp]),
     'cdr_kmeans_sqdist': (_i, [_vp, _l, _i, _i, _vp, _l, _vp, _vp, _vp]),
     'cdr_kmeans_update': (_i, [_vp, _l, _vp, _vp, _l, _i, _i, _vp, _vp]),
+    'cdr_kmeans_workspace_bytes': (_sz, [_i, _i, _i]),
+    'cdr_kmeans_fused_applicable': (_i, [_i, _i, _i]),
+    'cdr_kmeans_iterate_enqueue': (_i, [ctypes.POINTER(KmeansProblem), _vp]),
     'cdr_row_sqnorms': (_i, [_vp, _l, _i, _i, _vp, _vp]),
     'cdr_column_moments': (_i, [_vp, _l, _i, _i, _vp, _vp, _vp]),
     'cdr_center_columns': (_i, [_vp, _l, _i, _i, _vp, _d, _vp]),

@@ -102,7 +102,7 @@ class _AaEngine:
         self.update_scale_factors = update_scale_factors
         self.w_params = be.make_spg_params(weights_solver_kwargs)
         self.d_params = _dictionary_params(dictionary_solver_kwargs)
-        self.s_kwargs = dict(scale_factors_solver_kwargs or {})
+        self.s_params = _dictionary_params(dict(scale_factors_solver_kwargs or {}))
         self.lib = be.library()
 
         self.X = data_device if data_device is not None else be.to_device_padded(data)
@@ -325,30 +325,12 @@ class _AaEngine:
             self._cost_check(stage, end)
 
     def scale_factors_step(self):
-        """_update_kernel_aa_scale_factors (archetypal_analysis.py:243-258): a k-vector
-        SPG on k x k statistics; solved on the host with the generic spg()."""
-        st = self.state.read()
-        if st.done:
-            return
-        k, T, delta = self.k, self.T, self.delta
-        CKZ = self.CKZ.cpu().numpy()
-        ZtZ = self.ZtZ.cpu().numpy()
-        CKCt = self.CKCt.cpu().numpy()
-        trace = self.trace_data
-
-        def f(a):
-            a2 = np.outer(a, a)
-            return 0.5 * (trace - 2 * a.dot(np.diag(CKZ)) + np.sum(a2 * ZtZ * CKCt)) / T
-
-        def df(a):
-            return np.diag(ZtZ.dot(np.diag(a).dot(CKCt)) - CKZ) / T
-
-        def project(a):
-            return np.fmin(np.fmax(1.0 - delta, a), 1.0 + delta)
-
-        alpha = self.alpha.cpu().numpy()
-        alpha, _, _, _ = spg(f, df, alpha, project=project, **self.s_kwargs)
-        self.alpha.copy_(be.torch_mod().from_numpy(np.ascontiguousarray(alpha)))
+        """_update_kernel_aa_scale_factors (archetypal_analysis.py:243-258): the generic spg()
+        on the k-vector alpha over the box [1 - delta, 1 + delta], from three k x k
+        statistics -- one warp on the device (csrc/aa_steps.cu), no host round trip."""
+        be.check(self.lib.cdr_aa_scale_factors_step(
+            ctypes.byref(self.buf), ctypes.byref(self.s_params), float(self.delta),
+            be.stream_ptr()), 'cdr_aa_scale_factors_step')
         self._cost_check(1, False)
 
     def iteration(self):
@@ -365,8 +347,6 @@ class _AaEngine:
             self.weights_step()
 
     def graph_capturable(self):
-        if self.update_scale_factors and self.delta != 0:
-            return False
         if self.update_dictionary and self.d_params.max_iterations > _MAX_UNROLLED_SPG:
             return False
         return True

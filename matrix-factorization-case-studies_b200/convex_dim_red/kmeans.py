@@ -19,6 +19,8 @@ centre update is replicated.  FurthestSum seeding all-gathers the rows once and 
 slabs of the Gram matrix to the ranks.
 """
 
+import ctypes
+
 import numpy as np
 from sklearn.utils import check_random_state
 
@@ -71,8 +73,15 @@ def gather_rows(X, picks, comm=None):
     return out.cpu().numpy()
 
 
-def kmeans_lloyd(X, init_centres, tol=1e-4, max_iter=300, verbose=False, comm=None):
+def kmeans_lloyd(X, init_centres, tol=1e-4, max_iter=300, verbose=False, comm=None, stats=None,
+                 _time_iterations=0):
     """``KMeans(init=init_centres, n_init=1, algorithm='lloyd').fit(X)``.
+
+    ``stats`` (optional dict) receives ``loop_ms`` (the Lloyd iterations alone, CUDA events),
+    ``n_iter`` and ``device_loop`` (whether the graph-replayed device loop ran).
+    ``_time_iterations=N`` (bench.py) instead times N steady-state Lloyd iterations of the
+    device loop from the initial centres -- the state block is re-armed before each, so none
+    is skipped after convergence -- and returns the milliseconds per iteration.
 
     Returns ``(labels int32[T], centres k x d, inertia, n_iter)``.  With a process group X is
     this rank's row block and the labels are those of its rows; centres, inertia and n_iter
@@ -88,7 +97,9 @@ def kmeans_lloyd(X, init_centres, tol=1e-4, max_iter=300, verbose=False, comm=No
     if k > be.MAX_COMPONENTS:
         raise ValueError('n_clusters > %d is not supported by the B200 build' % be.MAX_COMPONENTS)
     s = be.stream_ptr
+    be.trace('kmeans: enter')
     Xd = be._upload_padded(X)          # private copy: it is centred in place below
+    be.trace('kmeans: upload')
     ldx = Xd.stride(0)
     ldt = be.round_up(T)
 
@@ -155,21 +166,15 @@ def kmeans_lloyd(X, init_centres, tol=1e-4, max_iter=300, verbose=False, comm=No
                                        labels.data_ptr(), dist.data_ptr(), s()),
                  'cdr_kmeans_sqdist')
 
-    strict = False
-    n_iter = 0
-    for it in range(max_iter):
-        n_iter = it + 1
-        e_step()
-        be.reduce_samples(onehot, ldt, 1, Xd, T, d, k, sums, ws)
-        comm.allreduce_sum(sums)
+    def m_step(host_counts):
+        """Centre update from `sums` / `counts` with the empty-cluster relocation of
+        _k_means_common.pyx:167-212 (rare, host logic); returns the total squared shift."""
         weights = counts.to(torch.float64)
-        host_counts = counts.cpu().numpy()
         if comm.enabled:
             if (host_counts == 0).any():
                 relocate_sharded(np.where(host_counts == 0)[0], weights)
         elif (host_counts == 0).any():
-            # _k_means_common.pyx:167-212 (rare): move empty clusters onto the samples
-            # farthest from their current centres
+            # move empty clusters onto the samples farthest from their current centres
             empty = np.where(host_counts == 0)[0]
             sq_distances()
             dh = dist.cpu().numpy()
@@ -186,16 +191,110 @@ def kmeans_lloyd(X, init_centres, tol=1e-4, max_iter=300, verbose=False, comm=No
         be.check(lib.cdr_kmeans_update(sums.data_ptr(), ldx, weights.data_ptr(),
                                        centres.data_ptr(), ldx, k, d, shift.data_ptr(), s()),
                  'cdr_kmeans_update')
+        sh = shift.cpu().numpy()
+        return float((np.sqrt(sh) ** 2).sum())           # _kmeans.py:733: (center_shift**2).sum()
+
+    strict = False
+    n_iter = 0
+    be.trace('kmeans: moments, centring, buffers')
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    fused = (not comm.enabled) and bool(lib.cdr_kmeans_fused_applicable(T, d, k))
+    if _time_iterations and not fused:
+        raise be.BackendError('the device Lloyd loop does not cover this shape')
+    if fused:
+        # device-resident loop (csrc/kmeans_iter.cu): five kernels per Lloyd iteration, the
+        # stopping rule on the device, replayed from a CUDA graph; the host reads the state
+        # block every few iterations and only steps in for an empty cluster
+        init = be.KmeansState()
+        init.max_iter = int(max_iter)
+        init.tol_abs = tol_abs
+        st_buf = torch.from_numpy(np.frombuffer(bytes(init), dtype=np.uint8).copy()).cuda()
+        wsb = torch.empty(lib.cdr_kmeans_workspace_bytes(T, d, k) // 8 + 1, dtype=torch.float64,
+                          device='cuda')
+        prob = be.KmeansProblem(
+            Xd.data_ptr(), ldx, T, d, k, centres.data_ptr(), labels.data_ptr(),
+            onehot.data_ptr(), ldt, sums.data_ptr(), cnorm.data_ptr(), shift.data_ptr(),
+            counts.data_ptr(), st_buf.data_ptr(), wsb.data_ptr(), wsb.numel() * 8)
+
+        def read_state():
+            return be.KmeansState.from_buffer_copy(st_buf.cpu().numpy().tobytes())
+
+        def write_state(st):
+            st_buf.copy_(torch.from_numpy(np.frombuffer(bytes(st), dtype=np.uint8).copy()))
+
+        def iterate():
+            be.check(lib.cdr_kmeans_iterate_enqueue(ctypes.byref(prob), s()),
+                     'cdr_kmeans_iterate_enqueue')
+
+        be.trace('kmeans: device loop set-up')
+        iterate()                                        # eager: warms every kernel up
+        st = read_state()
+        be.trace('kmeans: first iteration')
+        if _time_iterations:
+            armed = st_buf.clone()
+            armed.copy_(torch.from_numpy(np.frombuffer(bytes(init), dtype=np.uint8).copy()))
+
+            def one():
+                st_buf.copy_(armed)
+                iterate()
+            graph = be.capture_graph(one)
+            for _ in range(3):
+                graph.replay()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(int(_time_iterations)):
+                graph.replay()
+            t1.record()
+            torch.cuda.synchronize()
+            return t0.elapsed_time(t1) / int(_time_iterations)
+        graph, chunk = None, 1
+        while True:
+            if st.done and st.needs_relocation:
+                # the device stopped before the centre update: finish this iteration here
+                shift_tot = m_step(counts.cpu().numpy())
+                st.n_iter += 1
+                st.needs_relocation = 0
+                st.done = 0
+                if not st.changed:
+                    st.strict, st.done = 1, 1
+                elif shift_tot <= tol_abs or st.n_iter >= max_iter:
+                    st.done = 1
+                write_state(st)
+            if st.done:
+                break
+            if verbose:
+                print('Iteration %d, center shift %.6e' % (st.n_iter - 1, st.shift_total))
+            elif graph is None and not be.graphs_disabled():
+                graph = be.capture_graph(iterate)
+                be.trace('kmeans: graph capture')
+            for _ in range(1 if verbose else chunk):
+                if graph is not None:
+                    graph.replay()
+                else:
+                    iterate()
+            st = read_state()
+            chunk = min(2 * chunk, 16)
+        n_iter, strict = int(st.n_iter), bool(st.strict)
+    for it in (range(max_iter) if not fused else ()):
+        n_iter = it + 1
+        e_step()
+        be.reduce_samples(onehot, ldt, 1, Xd, T, d, k, sums, ws)
+        comm.allreduce_sum(sums)
+        shift_tot = m_step(counts.cpu().numpy())
         moved = int(changed.item())
         if not moved:
             strict = True
             break
-        sh = shift.cpu().numpy()
-        shift_tot = float((np.sqrt(sh) ** 2).sum())      # _kmeans.py:733: (center_shift**2).sum()
         if verbose:
             print('Iteration %d, center shift %.6e' % (it, shift_tot))
         if shift_tot <= tol_abs:
             break
+    ev1.record()
+    be.trace('kmeans: remaining iterations')
+    if stats is not None:
+        torch.cuda.synchronize()
+        stats.update(loop_ms=ev0.elapsed_time(ev1), n_iter=n_iter, device_loop=bool(fused))
     if not strict:
         e_step()                                         # _kmeans.py:745-757
     sq_distances()
@@ -205,7 +304,9 @@ def kmeans_lloyd(X, init_centres, tol=1e-4, max_iter=300, verbose=False, comm=No
     inertia = float(total.item())
     be.check(lib.cdr_center_columns(centres.data_ptr(), ldx, k, d, mean.data_ptr(), 1.0, s()),
              'cdr_center_columns')
-    return (labels.cpu().numpy(), be.to_host(centres, k, d), inertia, n_iter)
+    out = (labels.cpu().numpy(), be.to_host(centres, k, d), inertia, n_iter)
+    be.trace('kmeans: final E step, inertia, results to host')
+    return out
 
 
 def _row_sqnorms_and_device(X):

@@ -384,6 +384,150 @@ __global__ void __launch_bounds__(32) aa_cost_kernel(cdr_aa_buffers b, int stage
     }
 }
 
+// ======================================================================
+// Scale factors (delta != 0): _update_kernel_aa_scale_factors (archetypal_analysis.py:243-258)
+// = the generic spg() (spg.py:46-283) on the k-vector alpha with the box [1 - delta, 1 + delta]
+// as feasible set, objective and gradient from three k x k matrices
+//   f(a)  = 1/2 (tr K - 2 a.diag(CKZ) + sum_ij a_i a_j ZtZ_ij CKCt_ij) / n     (:221-229)
+//   df(a) = diag(ZtZ diag(a) CKCt - CKZ) / n                                    (:232-240)
+// with n = CKZ.shape[1] = k (the reference's `n_samples` there is the number of components).
+// One warp; lane l owns components l and l + 32.  M[i][j] = ZtZ_ij CKCt_ij and
+// N[i][j] = ZtZ_ij CKCt_ji live in shared memory.
+// ======================================================================
+__device__ __forceinline__ double sf_objective(const double* M, const double* cz, const double* a,
+                                               int k, double trace, int lane)
+{
+    double s = 0.0;
+    for (int i = lane; i < k; i += 32) {
+        double row = 0.0;
+        for (int j = 0; j < k; ++j) row = fma(M[i * k + j], a[j], row);
+        s += a[i] * (row - 2.0 * cz[i]);
+    }
+    s = warp_sum(s);
+    return 0.5 * (trace + s) / (double)k;
+}
+
+__device__ __forceinline__ void sf_gradient(const double* N, const double* cz, const double* a, int k,
+                                            double* g, int lane)
+{
+    for (int i = lane; i < k; i += 32) {
+        double row = 0.0;
+        for (int j = 0; j < k; ++j) row = fma(N[i * k + j], a[j], row);
+        g[i] = (row - cz[i]) / (double)k;
+    }
+}
+
+__global__ void __launch_bounds__(32)
+aa_scale_factors_kernel(cdr_aa_buffers b, cdr_spg_params p, double delta)
+{
+    cdr_loop_state* st = b.state;
+    if (*((volatile const int*)&st->done) != 0) return;
+    extern __shared__ double sf_sm[];
+    const int k = b.k, lane = threadIdx.x;
+    double* M = sf_sm;                    // k x k
+    double* N = M + k * k;                // k x k
+    double* cz = N + k * k;               // diag(CKZ)
+    double* x = cz + k;                   // iterate
+    double* xo = x + k;
+    double* g = xo + k;
+    double* d = g + k;
+    double* gn = d + k;
+    double* f_mem = gn + k;               // CDR_MAX_MEMORY
+    for (int idx = lane; idx < k * k; idx += 32) {
+        const int i = idx / k, j = idx % k;
+        M[idx] = b.ZtZ[idx] * b.CKCt[idx];
+        N[idx] = b.ZtZ[idx] * b.CKCt[j * k + i];
+    }
+    const double lo = 1.0 - delta, hi = 1.0 + delta;
+    for (int i = lane; i < k; i += 32) {
+        cz[i] = b.CKZ[i * k + i];
+        x[i] = fmin(fmax(lo, b.alpha[i]), hi);                 // spg.py:146-148
+    }
+    for (int i = lane; i < CDR_MAX_MEMORY; i += 32) f_mem[i] = 0.0;   // spg.py:153
+    __syncwarp();
+    const double trace = st->trace_data;
+    double f_old = sf_objective(M, cz, x, k, trace, lane);
+    int n_feval = 1;
+    double alpha = p.alpha0;
+    bool have_alpha = p.alpha0 > 0.0;                          // spg.py:151: alpha0 = None otherwise
+    bool converged = false;
+    int it = 0;
+    for (; it < p.max_iterations; ++it) {
+        for (int i = lane; i < k; i += 32) xo[i] = x[i];
+        sf_gradient(N, cz, x, k, g, lane);
+        __syncwarp();
+        if (!have_alpha) {
+            double m = 0.0;
+            for (int i = lane; i < k; i += 32)
+                m = fmax(m, fabs(fmin(fmax(lo, x[i] - g[i]), hi) - x[i]));
+            m = warp_max(m);
+            alpha = (fabs(m) > 1e-12) ? 1.0 / m : 1.0;
+            have_alpha = true;
+        }
+        double sdg = 0.0, sdd = 0.0;
+        for (int i = lane; i < k; i += 32) {
+            const double di = fmin(fmax(lo, x[i] - alpha * g[i]), hi) - x[i];
+            d[i] = di;
+            sdg = fma(di, g[i], sdg);
+            sdd = fma(di, di, sdd);
+        }
+        const double dlt = warp_sum(sdg);
+        const double dd = warp_sum(sdd);
+        // f_mem = roll(f_mem, 1); f_mem[0] = f_old; f_max = max(f_mem)   (spg.py:196-203)
+        double f_max = f_old;
+        if (lane == 0) {
+            for (int i = p.memory - 1; i > 0; --i) f_mem[i] = f_mem[i - 1];
+            f_mem[0] = f_old;
+        }
+        __syncwarp();
+        for (int i = 1; i < p.memory; ++i) f_max = fmax(f_max, f_mem[i]);
+        double lam = 1.0;
+        for (int i = lane; i < k; i += 32) x[i] = xo[i] + d[i];
+        __syncwarp();
+        double f_new = sf_objective(M, cz, x, k, trace, lane);
+        n_feval += 1;
+        while (f_new > f_max + p.gamma * lam * dlt) {
+            lam = spg_step_length(lam, dlt, f_old, f_new, p.sigma_one, p.sigma_two);
+            for (int i = lane; i < k; i += 32) x[i] = xo[i] + lam * d[i];
+            __syncwarp();
+            f_new = sf_objective(M, cz, x, k, trace, lane);
+            n_feval += 1;
+            if (fabs(lam) < p.lambda_min) {
+                if (lane == 0) st->spg_warnings |= 1;
+                break;
+            }
+        }
+        sf_gradient(N, cz, x, k, gn, lane);
+        __syncwarp();
+        double sdy = 0.0;
+        for (int i = lane; i < k; i += 32) sdy = fma(d[i], gn[i] - g[i], sdy);
+        const double sksk = lam * lam * dd;
+        const double betak = lam * warp_sum(sdy);
+        alpha = spg_cauchy_step(betak, sksk, p.alpha_min, p.alpha_max);
+        f_old = f_new;                       // spg.py:243 re-evaluates f at the same point
+        n_feval += 1;
+        double r2 = 0.0, rinf = 0.0;
+        for (int i = lane; i < k; i += 32) {
+            const double res = fmin(fmax(lo, x[i] - gn[i]), hi) - x[i];
+            r2 = fma(res, res, r2);
+            rinf = fmax(rinf, fabs(res));
+        }
+        r2 = warp_sum(r2);
+        rinf = warp_max(rinf);
+        converged = sqrt(r2) < p.epsilon_two;
+        if (p.use_infinity_norm) converged = converged || (rinf < p.epsilon_one);
+        if (converged) break;
+        if (n_feval > p.max_feval) {
+            if (lane == 0) st->spg_warnings |= 2;
+            break;
+        }
+    }
+    if (it >= p.max_iterations - 1 && !converged && lane == 0 && p.max_iterations > 0)
+        st->spg_warnings |= 4;               // spg.py:277-281
+    __syncwarp();
+    for (int i = lane; i < k; i += 32) b.alpha[i] = x[i];
+}
+
 static int row_threads(int T)
 {
     if (T <= 2048) return 256;
@@ -477,6 +621,20 @@ extern "C" int cdr_aa_spg_update(const cdr_aa_buffers* b, const cdr_spg_params* 
     aa_spg_post_kernel<<<b->k, row_threads(b->T), smem, s>>>(*b, compute_residual);
     CDR_RETURN_IF_LAUNCH_FAILED();
     aa_spg_finish_kernel<<<1, 1, 0, s>>>(*b, *p, compute_residual);
+    CDR_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+extern "C" int cdr_aa_scale_factors_step(const cdr_aa_buffers* b, const cdr_spg_params* p, double delta,
+                                         cdr_stream_t stream)
+{
+    CDR_AA_CHECK(b);
+    CDR_CHECK_ARG(p != nullptr && delta >= 0.0);
+    if (p->memory < 1 || p->memory > CDR_MAX_MEMORY) return CDR_ERR_UNSUPPORTED;
+    const size_t smem = (2 * (size_t)b->k * b->k + 6 * (size_t)b->k + CDR_MAX_MEMORY) * sizeof(double);
+    int rc = set_smem<aa_scale_factors_kernel>(smem);
+    if (rc) return rc;
+    aa_scale_factors_kernel<<<1, 32, smem, (cudaStream_t)stream>>>(*b, *p, delta);
     CDR_RETURN_IF_LAUNCH_FAILED();
     return 0;
 }

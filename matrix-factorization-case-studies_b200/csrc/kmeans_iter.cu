@@ -1,0 +1,219 @@
+// One Lloyd iteration of k-means behind a single C call (cdr_kmeans_iterate_enqueue), with
+// the stopping rule on the device, so that the host replays a captured CUDA graph and only
+// looks at the 48-byte state block every few iterations.
+//
+// The reference's drivers call scikit-learn's KMeans (bin/run_hadisst_kmeans.py:128-131);
+// semantics are those of scikit-learn 1.9.0's `_kmeans_single_lloyd` (_kmeans.py:620-760,
+// _k_means_lloyd.pyx:193-218, _k_means_common.pyx:167-262), see kmeans.cu.  Per iteration:
+//
+//   1. kmeans_begin_kernel     ||c_j||^2 of the centres, counters cleared
+//   2. reduce over features    centres . samples as per-strip partials (stream_tma.cu)
+//   3. kmeans_assign_kernel    per sample: sum of the strip partials, score_j = ||c_j||^2 -
+//                              2 x.c_j, FIRST minimum (strict <), one-hot row, cluster sizes,
+//                              "a label changed" flag
+//   4. reduce over samples     per-cluster sums = one_hot' X  (stream_tma.cu)
+//   5. kmeans_update_kernel    centres = sums / n_j, squared shift per centre; the last CTA
+//                              applies the stopping rule (labels unchanged -> strict
+//                              convergence; total shift <= tol; iteration limit).
+//
+// An empty cluster (rare) stops the device loop before the centre update with
+// state->needs_relocation set; the host relocates (_k_means_common.pyx:167-212), finishes
+// that iteration with the stand-alone calls of kmeans.cu and resumes.  Small shapes, which
+// the strip kernels do not cover, run the stand-alone calls only.
+#include "cdr_common.cuh"
+
+namespace cdr {
+
+__device__ __forceinline__ bool km_done(const cdr_kmeans_state* st)
+{
+    return *((volatile const int*)&st->done) != 0;
+}
+
+// 1. squared norms of the centres (one CTA per centre); counters cleared
+__global__ void __launch_bounds__(256)
+kmeans_begin_kernel(const double* __restrict__ C, long ldc, int d, int k, double* cnorm, int* counts,
+                    cdr_kmeans_state* st)
+{
+    if (km_done(st)) return;
+    __shared__ double scratch[32];
+    const double* row = C + (long)blockIdx.x * ldc;
+    double s[1] = {0.0};
+    for (int f = threadIdx.x; f < d; f += blockDim.x) s[0] = fma(row[f], row[f], s[0]);
+    block_sum<1>(s, scratch);
+    if (threadIdx.x == 0) {
+        cnorm[blockIdx.x] = s[0];
+        counts[blockIdx.x] = 0;
+        if (blockIdx.x == 0) st->changed = 0;
+    }
+}
+
+// 3. assignment from the per-strip partials part[strip][t][8] (k <= 8): an aligned group of 8
+// lanes owns a sample, lane c component c; the four groups of a warp split the strips of one
+// sample and combine in fixed order
+__global__ void __launch_bounds__(256)
+kmeans_assign_kernel(const double* __restrict__ part, int nstrips, const double* __restrict__ cnorm,
+                     int T, int k, int32_t* labels, double* onehot, long ldo, int* counts,
+                     cdr_kmeans_state* st)
+{
+    if (km_done(st)) return;
+    const int lane = threadIdx.x & 31, g = lane & 7, q = lane >> 3;
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // one sample per warp
+    if (t >= T) return;
+    double a0 = 0.0, a1 = 0.0;
+    {
+        const double* base = part + ((long)q * T + t) * 8 + g;
+        const long stride = 4L * T * 8;
+        const int n = (nstrips - q + 3) / 4;
+        int i = 0;
+        for (; i + 8 <= n; i += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(base + (long)(i + u) * stride);
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) {
+                a0 += v[u];
+                a1 += v[u + 1];
+            }
+        }
+        for (; i < n; ++i) a0 += __ldcg(base + (long)i * stride);
+    }
+    const double v = a0 + a1;
+    // x.c_j: the four strip phases in fixed order
+    double dot = __shfl_sync(CDR_FULL_MASK, v, g);
+    dot += __shfl_sync(CDR_FULL_MASK, v, g + 8);
+    dot += __shfl_sync(CDR_FULL_MASK, v, g + 16);
+    dot += __shfl_sync(CDR_FULL_MASK, v, g + 24);
+    double score = (g < k) ? cnorm[g] - 2.0 * dot : INFINITY;
+    int idx = g;
+    // first minimum over the 8 components: the smaller score wins, the lower index on a tie
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        const double os = __shfl_xor_sync(CDR_FULL_MASK, score, o, 8);
+        const int oi = __shfl_xor_sync(CDR_FULL_MASK, idx, o, 8);
+        if (os < score || (os == score && oi < idx)) {
+            score = os;
+            idx = oi;
+        }
+    }
+    if (q == 0) {
+        if (g < k) onehot[(long)g * ldo + t] = (g == idx) ? 1.0 : 0.0;
+        if (g == 0) {
+            if (labels[t] != idx) {
+                labels[t] = idx;
+                atomicOr(&st->changed, 1);
+            }
+            atomicAdd(&counts[idx], 1);
+        }
+    }
+}
+
+// 5. centres <- sums * (1 / count), squared shift per centre (one CTA per centre); the last
+// CTA applies the stopping rule of _kmeans.py:703-743
+__global__ void __launch_bounds__(256)
+kmeans_update_kernel(const double* __restrict__ sums, long lds, const int* __restrict__ counts,
+                     double* centres, long ldc, int d, int k, double* shift, cdr_kmeans_state* st)
+{
+    if (km_done(st)) return;
+    __shared__ double scratch[32];
+    __shared__ int empty;
+    if (threadIdx.x == 0) {
+        int e = 0;
+        for (int j = 0; j < k; ++j) e |= (counts[j] == 0);
+        empty = e;
+    }
+    __syncthreads();
+    if (empty) {
+        // the host relocates the empty cluster(s) and finishes this iteration
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            st->needs_relocation = 1;
+            __threadfence();
+            st->done = 1;
+        }
+        return;
+    }
+    const int j = blockIdx.x;
+    const double alpha = 1.0 / (double)counts[j];
+    double s[1] = {0.0};
+    for (int f = threadIdx.x; f < d; f += blockDim.x) {
+        const double nv = sums[(long)j * lds + f] * alpha;
+        const double df = nv - centres[(long)j * ldc + f];
+        s[0] = fma(df, df, s[0]);
+        centres[(long)j * ldc + f] = nv;
+    }
+    block_sum<1>(s, scratch);
+    if (threadIdx.x != 0) return;
+    shift[j] = s[0];
+    __threadfence();
+    if (atomicAdd(&st->ticket, 1u) != gridDim.x - 1) return;
+    __threadfence();
+    st->ticket = 0u;
+    double total = 0.0;
+    for (int i = 0; i < k; ++i) {
+        const double r = sqrt(__ldcg(shift + i));       // _kmeans.py:733: (center_shift ** 2).sum()
+        total += r * r;
+    }
+    st->shift_total = total;
+    st->n_iter += 1;
+    if (st->changed == 0) {
+        st->strict = 1;
+        st->done = 1;
+    } else if (total <= st->tol_abs || st->n_iter >= st->max_iter) {
+        st->done = 1;
+    }
+}
+
+}  // namespace cdr
+
+using namespace cdr;
+
+extern "C" size_t cdr_kmeans_workspace_bytes(int T, int d, int k)
+{
+    if (T < 1 || d < 1 || k < 1 || k > CDR_MAX_COMPONENTS) return 0;
+    const size_t s1 = cdr_reduce_samples_workspace_bytes(T, d, k);
+    const size_t s2 = cdr_reduce_features_workspace_bytes(T, d, k);
+    return (s1 > s2 ? s1 : s2) + 256;
+}
+
+extern "C" int cdr_kmeans_fused_applicable(int T, int d, int k)
+{
+    if (k > 8) return 0;
+    int out[12];
+    tma_stream_plan(T, d, k, 0, out);
+    int TC, nstrips;
+    return (out[0] && out[5] && features_strip_geometry(T, d, k, &TC, &nstrips)) ? 1 : 0;
+}
+
+extern "C" int cdr_kmeans_iterate_enqueue(const cdr_kmeans_problem* p, cdr_stream_t stream)
+{
+    CDR_CHECK_ARG(p != nullptr && p->X && p->centres && p->labels && p->onehot && p->sums &&
+                  p->cnorm && p->shift && p->counts && p->state);
+    CDR_CHECK_ARG(p->T >= 1 && p->d >= 1 && p->k >= 1 && p->ldt >= p->T);
+    if (!cdr_kmeans_fused_applicable(p->T, p->d, p->k)) return CDR_ERR_NOT_APPLICABLE;
+    if (p->workspace == nullptr || p->workspace_bytes < cdr_kmeans_workspace_bytes(p->T, p->d, p->k))
+        return CDR_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int T = p->T, d = p->d, k = p->k;
+    const cdr_flags* flags = reinterpret_cast<const cdr_flags*>(p->state);   // `done` comes first
+    int TC = 0, nstrips = 0;
+    features_strip_geometry(T, d, k, &TC, &nstrips);
+
+    kmeans_begin_kernel<<<k, 256, 0, s>>>(p->centres, p->ldx, d, k, p->cnorm, p->counts, p->state);
+    CDR_RETURN_IF_LAUNCH_FAILED();
+    {
+        const int rc = run_reduce_features_tma(p->centres, p->ldx, p->X, p->ldx, T, d, k, nullptr, 0,
+                                               p->workspace, p->workspace_bytes, flags, s, nullptr);
+        if (rc != 0) return rc == CDR_TMA_NOT_APPLICABLE ? CDR_ERR_NOT_APPLICABLE : rc;
+    }
+    kmeans_assign_kernel<<<(T + 7) / 8, 256, 0, s>>>((const double*)p->workspace, nstrips, p->cnorm, T, k,
+                                                     p->labels, p->onehot, p->ldt, p->counts, p->state);
+    CDR_RETURN_IF_LAUNCH_FAILED();
+    {
+        const int rc = cdr_reduce_samples(p->onehot, p->ldt, 1, p->X, p->ldx, T, d, k, nullptr, p->sums,
+                                          p->ldx, p->workspace, p->workspace_bytes, flags, s);
+        if (rc != 0) return rc;
+    }
+    kmeans_update_kernel<<<k, 256, 0, s>>>(p->sums, p->ldx, p->counts, p->centres, p->ldx, d, k,
+                                           p->shift, p->state);
+    CDR_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}

@@ -220,11 +220,21 @@ samples64_kernel(const double* __restrict__ Lp, long sLi, const double* __restri
             g64_cp16(xs + r * kS64RSX + cpos, X + (long)t * ldx + f);
         }
         if (ZLAYOUT) {
-            // weights rows t0 .. t0+16, k doubles each (k may be odd: 8-byte pieces)
-            for (int e = tid; e < kG64KC * 64; e += kG64Threads) {
-                const int r = e >> 6, i = e & 63;
-                const int t = t0 + r;
-                if (i < k && t < t_end) g64_cp8(ls + r * kS64RSZ + i, Lp + (long)t * k + i);
+            // weights rows t0 .. t0+16, k doubles each: 16-byte pieces when k is even (sLi is
+            // abused as that flag here: the row stride of this layout is always 1), 8-byte
+            // pieces otherwise
+            if (sLi == 2) {
+                for (int e = tid; e < kG64KC * 32; e += kG64Threads) {
+                    const int r = e >> 5, i = (e & 31) * 2;
+                    const int t = t0 + r;
+                    if (i < k && t < t_end) g64_cp16(ls + r * kS64RSZ + i, Lp + (long)t * k + i);
+                }
+            } else {
+                for (int e = tid; e < kG64KC * 64; e += kG64Threads) {
+                    const int r = e >> 6, i = e & 63;
+                    const int t = t0 + r;
+                    if (i < k && t < t_end) g64_cp8(ls + r * kS64RSZ + i, Lp + (long)t * k + i);
+                }
             }
         } else {
             // rows i of L, 16 doubles (128 bytes) of the t axis each: 512 16-byte pieces
@@ -466,7 +476,8 @@ int run_reduce_samples64(const double* Lp, long sLi, long sLt, const double* X, 
     }
     if (zlayout)
         samples64_kernel<true><<<nstrips * nsplit, kG64Threads, kS64Smem, stream>>>(
-            Lp, sLi, X, ldx, T, k, dpad, nsplit, per, (double*)workspace, flags);
+            Lp, (k % 2 == 0 && (((uintptr_t)Lp) & 15) == 0) ? 2 : 1, X, ldx, T, k, dpad, nsplit, per,
+            (double*)workspace, flags);
     else
         samples64_kernel<false><<<nstrips * nsplit, kG64Threads, kS64Smem, stream>>>(
             Lp, sLi, X, ldx, T, k, dpad, nsplit, per, (double*)workspace, flags);

@@ -435,6 +435,7 @@ def workload_block(args, workload, X, Xd, rank, world, comm, sampler, hbm_peak, 
             'reduce_samples_gbs': pass_bytes / (t_s * 1e-3) / 1e9,
             'reduce_features_gbs': pass_bytes / (t_f * 1e-3) / 1e9,
             'qp_batched_ms': t_qp, 'passes_per_step': passes, 'step_ms': ms,
+            'non_streaming_ms_per_step': ms - passes / 2.0 * (t_s + t_f),
             'streaming_share_of_step': passes / 2.0 * (t_s + t_f) / ms,
             'whole_step_gbs': passes * pass_bytes / (ms * 1e-3) / 1e9,
             'whole_step_frac_of_hbm_peak': passes * pass_bytes / (ms * 1e-3) / 1e9 / hbm_peak}

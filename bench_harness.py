@@ -125,17 +125,21 @@ def time_passes(args, workload, eng, T, d, k):
         t_samples = time_launches(lambda: be.reduce_samples(
             eng.Z, 1, k, eng.X, T, d, k, eng.WT, ws, E=eng.P if k <= 16 else None))
         t_features = time_launches(lambda: be.reduce_features(eng.WT, eng.X, T, d, k, eng.XWt, ws))
-        zsave = eng.Z.clone()
-        t_qp = time_launches(lambda: (eng.Z.copy_(zsave), be.quad_simplex_spg_batched(
-            eng.WtW, None, eng.XWt, 1, eng.ldt, eng.Z, T, k, eng.params)), reps=5)
+        t_qp = None          # fused into gpnh_weights_fused_kernel (not callable on its own)
+        if not getattr(eng, 'c_loop', False):
+            zsave = eng.Z.clone()
+            t_qp = time_launches(lambda: (eng.Z.copy_(zsave), be.quad_simplex_spg_batched(
+                eng.WtW, None, eng.XWt, 1, eng.ldt, eng.Z, T, k, eng.params)), reps=5)
         passes = 2
     else:
         t_samples = time_launches(lambda: be.reduce_samples(
             eng.D, eng.ldt, 1, eng.X, T, d, k, eng.tmp_kd, ws))
         t_features = time_launches(lambda: be.reduce_features(eng.tmp_kd, eng.X, T, d, k, eng.DK, ws))
-        zsave = eng.Z.clone()
-        t_qp = time_launches(lambda: (eng.Z.copy_(zsave), be.quad_simplex_spg_batched(
-            eng.CKCt, eng.alpha, eng.CK, 1, eng.ldt, eng.Z, T, k, eng.w_params)), reps=5)
+        t_qp = None          # fused into aa_weights_fused_kernel
+        if not getattr(eng, 'c_loop', False):
+            zsave = eng.Z.clone()
+            t_qp = time_launches(lambda: (eng.Z.copy_(zsave), be.quad_simplex_spg_batched(
+                eng.CKCt, eng.alpha, eng.CK, 1, eng.ldt, eng.Z, T, k, eng.w_params)), reps=5)
         passes = 4
     return t_samples, t_features, t_qp, passes
 

@@ -1,7 +1,12 @@
-"""Model check of the flag protocols of the peer-memory collectives (csrc/peer.cuh,
+"""Model check of the synchronisation protocols of the peer-memory collectives (csrc/peer.cuh,
 csrc/peer.cu, the SamplesExchange variant in csrc/stream_tma.cu) -- no GPU involved.
 
-The CUDA kernels synchronise GPUs with epoch flags in each other's memory.  Whether such a
+The CUDA kernels synchronise GPUs through each other's memory: the stand-alone collectives
+with epoch flags around the data (st.release.sys / ld.acquire.sys), the fused
+reduce-over-samples + all-reduce kernel and the one-shot exchanges in the kernel tails with
+"tagged words" -- every 8-byte word carries 32 data bits and the 32-bit epoch of its exchange,
+so data and flag are one store, the reader polls the words themselves, and two buffer sets
+alternate by epoch parity.  Whether such a
 protocol can deadlock, read a tile of the wrong launch, or overwrite data a slower rank
 still needs does not depend on CUDA: it is a property of the order of flag and data
 accesses.  This file restates that order as Python generators (one per CTA, one `yield`
@@ -39,50 +44,85 @@ class Region:
         # all-gather of column blocks
         self.gathered = [0] * world                                 # block of rank r -> launch
         self.gather_readers = 0
+        # tagged-word buffers (two sets by epoch parity): tile inbox [set][from][strip], result
+        # buffer [set][strip], small-exchange slots [set][from]; value = epoch tag, and whether
+        # the current content has been read by its consumer
+        self.ll_inbox = [[[0] * max_strips for _ in range(world)] for _ in range(2)]
+        self.ll_inbox_read = [[[True] * max_strips for _ in range(world)] for _ in range(2)]
+        self.ll_res = [[0] * max_strips for _ in range(2)]
+        self.ll_res_read = [[True] * max_strips for _ in range(2)]
+        self.small_epoch = 0
+        self.small_ll = [[0] * world for _ in range(2)]
+        self.small_read = [[True] * world for _ in range(2)]
 
 
 def fused_cta(mem, world, rank, cta, grid, nstrips):
-    """One CTA of reduce_samples_tma_kernel<..., SamplesExchange> (consumer warps)."""
+    """One CTA of reduce_samples_tma_kernel<..., SamplesExchange> (consumer warps): tagged
+    words, no flags, no fences (stream_tma.cu)."""
     mine = mem[rank]
     epoch = mine.fused_epoch + 1
+    cur = epoch & 1
     yield
     strips = range(cta, nstrips, grid)
     for strip in strips:
         yield                                                   # accumulate the strip
         owner = strip % world
-        # push the tile into this rank's slot of the owner's inbox
-        assert mem[owner].consumed[rank][strip], 'tile overwritten before the owner read it'
-        mem[owner].inbox[rank][strip] = epoch
-        mem[owner].consumed[rank][strip] = False
-        yield
-        mem[owner].ready[strip][rank] = epoch                   # st.release.sys
+        # the epilogue pushes the tagged tile into this rank's slot of the owner's inbox
+        assert mem[owner].ll_inbox_read[cur][rank][strip], 'tile overwritten before the owner read it'
+        mem[owner].ll_inbox[cur][rank][strip] = epoch
+        mem[owner].ll_inbox_read[cur][rank][strip] = False
         yield
         if owner == rank:
             for r in range(world):
-                while mine.ready[strip][r] < epoch:             # ld.acquire.sys
+                while mine.ll_inbox[cur][r][strip] != epoch:    # poll the words of rank r's tile
                     yield
-            for r in range(world):
-                assert mine.inbox[r][strip] == epoch, 'tile of another launch in the sum'
-                mine.consumed[r][strip] = True
+                mine.ll_inbox_read[cur][r][strip] = True
                 yield
-            for r in range(world):
-                assert mem[r].out_readers == 0 or mem[r].out[strip] == epoch, \
-                    'sum pushed while a later kernel of the previous launch still reads out'
-                mem[r].out[strip] = epoch
-                yield
-            for r in range(world):
-                mem[r].done[strip] = epoch                      # st.release.sys
-                yield
-    for strip in strips:
-        while mine.done[strip] < epoch:
+            assert mine.out_readers == 0 or mine.out[strip] == epoch, \
+                'sum stored while a later kernel of the previous launch still reads out'
+            mine.out[strip] = epoch
             yield
-        assert mine.out[strip] == epoch
+            for r in range(world):
+                if r != rank:
+                    assert mem[r].ll_res_read[cur][strip], 'result overwritten before it was read'
+                    mem[r].ll_res[cur][strip] = epoch
+                    mem[r].ll_res_read[cur][strip] = False
+                    yield
+    for strip in strips:
+        if strip % world == rank:
+            continue
+        while mine.ll_res[cur][strip] != epoch:                 # poll the result words
+            yield
+        mine.ll_res_read[cur][strip] = True
+        assert mine.out_readers == 0 or mine.out[strip] == epoch
+        mine.out[strip] = epoch
+        yield
     # the last CTA to leave publishes the epoch
     mine.fused_tickets += 1
     if mine.fused_tickets == grid:
         mine.fused_tickets = 0
         yield
         mine.fused_epoch = epoch
+    yield
+
+
+def small_cta(mem, world, rank):
+    """peer::cta_allreduce_small: the last CTA of a fused kernel exchanges its rank's sums."""
+    mine = mem[rank]
+    epoch = mine.small_epoch + 1
+    cur = epoch & 1
+    yield
+    for r in range(world):
+        assert mem[r].small_read[cur][rank], 'statistics overwritten before the peer read them'
+        mem[r].small_ll[cur][rank] = epoch
+        mem[r].small_read[cur][rank] = False
+        yield
+    for r in range(world):
+        while mine.small_ll[cur][r] != epoch:
+            yield
+        mine.small_read[cur][r] = True
+        yield
+    mine.small_epoch = epoch
     yield
 
 
@@ -185,6 +225,8 @@ def rank_stream(mem, world, rank, plan, rng):
         if kind == 'fused':
             kernels = [[fused_cta(mem, world, rank, b, grid, size) for b in range(grid)],
                        [reader_kernel(mem, rank, size, launch_of(plan, launch, 'fused'))]]
+        elif kind == 'small':
+            kernels = [[small_cta(mem, world, rank)]]
         elif kind == 'allgather':
             kernels = [[allgather_cta(mem, world, rank, b, grid, launch) for b in range(grid)],
                        [gather_reader_kernel(mem, world, rank, launch)]]
@@ -236,6 +278,22 @@ def test_fused_exchange_protocol(world):
     for seed in range(20):
         run(world, plan, seed, bias=[1] + [25] * (world - 1))
         run(world, plan, seed, bias=[25] * (world - 1) + [1])
+
+
+@pytest.mark.parametrize('world', [2, 3, 8])
+def test_tagged_word_exchanges_as_in_a_sharded_iteration(world):
+    """The sharded GPNH iteration (fused k x d exchange, then the statistics exchange in the
+    weights kernel's tail) and the AA one (two fused exchanges and three small ones), with
+    ranks of very different speed and with fewer strips than ranks."""
+    gpnh = [('fused', 4, 9), ('small', 1, 0)] * 5
+    aa = [('fused', 3, 9), ('small', 1, 0), ('small', 1, 0), ('fused', 3, 9), ('small', 1, 0)] * 3
+    few = [('fused', 2, 2), ('small', 1, 0)] * 4            # some ranks own no strip
+    for plan in (gpnh, aa, few):
+        for seed in range(12):
+            mem = run(world, plan, seed)
+            assert all(m.small_epoch == sum(1 for k, _, _ in plan if k == 'small') for m in mem)
+            run(world, plan, seed, bias=[1] + [30] * (world - 1))
+            run(world, plan, seed, bias=[30] * (world - 1) + [1])
 
 
 def test_fused_exchange_survives_a_change_of_grid():

@@ -306,8 +306,9 @@ int cdr_center_columns(double* X, long ldx, int T, int d, const double* mean, do
 
 /* One Lloyd iteration (scikit-learn `_kmeans_single_lloyd`, _kmeans.py:620-760) behind one
  * call, stopping rule on the device: E step from the per-strip partials of centres . X', the
- * per-cluster sums as one_hot' X, centre update and the tests "labels unchanged" / "total
- * shift <= tol" / iteration limit by the last CTA (csrc/kmeans_iter.cu).  X is the centred
+ * per-cluster sums as one_hot' X, centre update (with the next ||c_j||^2) and the tests "labels
+ * unchanged" / "total shift <= tol" / iteration limit by the last CTA (csrc/kmeans_iter.cu):
+ * four kernels.  X is the centred
  * data; `counts` is int[k]; the state block starts zeroed except max_iter and tol_abs.  An
  * empty cluster stops the loop before the centre update with needs_relocation set (the caller
  * relocates and finishes that iteration with the stand-alone calls above).  Returns
@@ -344,6 +345,9 @@ typedef struct cdr_kmeans_problem {
 
 size_t cdr_kmeans_workspace_bytes(int T, int d, int k);
 int cdr_kmeans_fused_applicable(int T, int d, int k);
+/* ||c_j||^2 of the current centres, counters cleared: before the first iteration and after the
+ * caller changed the centres itself */
+int cdr_kmeans_prepare_enqueue(const cdr_kmeans_problem* problem, cdr_stream_t stream);
 int cdr_kmeans_iterate_enqueue(const cdr_kmeans_problem* problem, cdr_stream_t stream);
 
 /* ------------------------------------------------------------------ peer-memory collectives

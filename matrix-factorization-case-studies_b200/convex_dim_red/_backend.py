@@ -196,6 +196,7 @@ SIGNATURES = {
     'cdr_kmeans_update': (_i, [_vp, _l, _vp, _vp, _l, _i, _i, _vp, _vp]),
     'cdr_kmeans_workspace_bytes': (_sz, [_i, _i, _i]),
     'cdr_kmeans_fused_applicable': (_i, [_i, _i, _i]),
+    'cdr_kmeans_prepare_enqueue': (_i, [ctypes.POINTER(KmeansProblem), _vp]),
     'cdr_kmeans_iterate_enqueue': (_i, [ctypes.POINTER(KmeansProblem), _vp]),
     'cdr_row_sqnorms': (_i, [_vp, _l, _i, _i, _vp, _vp]),
     'cdr_column_moments': (_i, [_vp, _l, _i, _i, _vp, _vp, _vp]),

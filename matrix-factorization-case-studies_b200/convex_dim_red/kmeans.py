@@ -227,6 +227,12 @@ def kmeans_lloyd(X, init_centres, tol=1e-4, max_iter=300, verbose=False, comm=No
             be.check(lib.cdr_kmeans_iterate_enqueue(ctypes.byref(prob), s()),
                      'cdr_kmeans_iterate_enqueue')
 
+        def prepare():
+            be.check(lib.cdr_kmeans_prepare_enqueue(ctypes.byref(prob), s()),
+                     'cdr_kmeans_prepare_enqueue')
+
+        prepare()
+
         be.trace('kmeans: device loop set-up')
         iterate()                                        # eager: warms every kernel up
         st = read_state()
@@ -238,6 +244,7 @@ def kmeans_lloyd(X, init_centres, tol=1e-4, max_iter=300, verbose=False, comm=No
             def one():
                 st_buf.copy_(armed)
                 iterate()
+            prepare()
             graph = be.capture_graph(one)
             for _ in range(3):
                 graph.replay()
@@ -260,7 +267,9 @@ def kmeans_lloyd(X, init_centres, tol=1e-4, max_iter=300, verbose=False, comm=No
                     st.strict, st.done = 1, 1
                 elif shift_tot <= tol_abs or st.n_iter >= max_iter:
                     st.done = 1
+                st.changed = 0
                 write_state(st)
+                prepare()                                # the centres changed on this side
             if st.done:
                 break
             if verbose:

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 reduce_samples_tma_kernel(const double* __restrict__ Lp, long sLi, long sLt,
                           const double* __restrict__ X, long ldx, int T, int dpad, int k, int TC,
                           int nstrips, int stages, const double* __restrict__ E,
-                          double* __restrict__ out, long ldo, const cdr_flags* flags,
+                          double* __restrict__ out, long ldo, const cdr_flags* flags, int keep_from,
                           Exchange xch = Exchange())
 {
     if (is_done(flags)) return;
@@ -81,6 +81,7 @@ reduce_samples_tma_kernel(const double* __restrict__ Lp, long sLi, long sLt,
         // ------------------------------ producer warp: lane 0 owns the barriers, every
         // lane issues the bulk copy of one row (a single thread issuing all copies of a
         // stage is limited by the per-instruction issue latency, not by bytes)
+        const uint64_t pol_last = l2_policy_evict_last(), pol_first = l2_policy_evict_first();
         int it = 0;
         for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
             const int c0 = strip * TC;
@@ -96,8 +97,10 @@ reduce_samples_tma_kernel(const double* __restrict__ Lp, long sLi, long sLt,
                 __syncwarp();
                 if (lane < rows) {
                     double* dst = tiles + s * stage_doubles + (long)lane * RS;
-                    const double* src = X + (long)(rt * kSampTR + lane) * ldx + c0;
-                    bulk_g2s(dst, src, (uint32_t)(w * 8), &pipe.full[s]);
+                    const int row = rt * kSampTR + lane;
+                    const double* src = X + (long)row * ldx + c0;
+                    bulk_g2s_hint(dst, src, (uint32_t)(w * 8), &pipe.full[s],
+                                  row >= keep_from ? pol_last : pol_first);
                 }
             }
         }
@@ -347,7 +350,8 @@ template <int KT, int MAXUQ>
 __global__ void __launch_bounds__(kThreads, 1)
 reduce_features_strip_kernel(const double* __restrict__ M, long ldm, const double* __restrict__ X,
                              long ldx, int T, int dpad, int k, int TC, int nstrips, int stages,
-                             double* __restrict__ part, const cdr_flags* flags, StripGram gram)
+                             double* __restrict__ part, const cdr_flags* flags, StripGram gram,
+                             int keep_from)
 {
     if (is_done(flags)) return;
     constexpr int KP = 8 * KT;
@@ -366,6 +370,7 @@ reduce_features_strip_kernel(const double* __restrict__ M, long ldm, const doubl
     const int ntiles = (T + kFsTR - 1) / kFsTR;
 
     if (warp == kConsumerWarps) {
+        const uint64_t pol_last = l2_policy_evict_last(), pol_first = l2_policy_evict_first();
         int it = 0;
         for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
             const int c0 = strip * TC;
@@ -381,9 +386,10 @@ reduce_features_strip_kernel(const double* __restrict__ M, long ldm, const doubl
                 }
                 __syncwarp();
                 if (lane < rows)
-                    bulk_g2s(tiles + s * stage_doubles + (long)lane * RS,
-                             X + (long)(tile * kFsTR + lane) * ldx + c0, (uint32_t)(w * 8),
-                             &pipe.full[s]);
+                    bulk_g2s_hint(tiles + s * stage_doubles + (long)lane * RS,
+                                  X + (long)(tile * kFsTR + lane) * ldx + c0, (uint32_t)(w * 8),
+                                  &pipe.full[s],
+                                  tile * kFsTR + lane >= keep_from ? pol_last : pol_first);
             }
         }
         return;
@@ -607,6 +613,24 @@ static bool tma_disabled()
 
 constexpr size_t kSmemBudget = 220 * 1024;
 
+// First row of the band of X that the strip kernels copy with evict_last (rows >= it; the
+// others with evict_first).  Measured on B200 at HadISST shape (profiles/r02/
+// r02s_l2_band_sweep.txt): marking ALL of X evict_first -- streaming data that will not be
+// re-read before it is evicted anyway, so it should not displace the partials and the small
+// replicated matrices -- makes the passes 2-8 % faster (100 / 102 -> 98 / 94 us); an
+// evict_last band of 48-112 MB brought no L2 hits on top of that, so the default band is
+// empty.  CDR_L2_RESIDENT_MB sets a band size for experiments.
+static int l2_resident_from_row(int T, int dpad)
+{
+    static long band_bytes = -1;
+    if (band_bytes < 0) {
+        const char* e = getenv("CDR_L2_RESIDENT_MB");
+        band_bytes = (e != nullptr ? atol(e) : 0L) * 1000000L;
+    }
+    const long rows = band_bytes / ((long)dpad * 8);
+    return rows >= T ? 0 : T - (int)rows;
+}
+
 template <auto Kern>
 static int ensure_smem(size_t smem)
 {
@@ -670,7 +694,8 @@ static int launch_samples_tma(const double* Lp, long sLi, long sLt, const double
     if (rc) return rc;
     const int grid = nstrips < sm_count() ? nstrips : sm_count();
     reduce_samples_tma_kernel<KT, MAXU, FUSE_E><<<grid, kThreads, smem, stream>>>(
-        Lp, sLi, sLt, X, ldx, T, dpad, k, TC, nstrips, stages, E, out, ldo, flags);
+        Lp, sLi, sLt, X, ldx, T, dpad, k, TC, nstrips, stages, E, out, ldo, flags,
+        l2_resident_from_row(T, dpad));
     CDR_RETURN_IF_LAUNCH_FAILED();
     return 0;
 }
@@ -723,7 +748,8 @@ static int launch_samples_exchange(const cdr_peer_group& g, size_t out_offset, c
     xch.g = g;
     xch.out_offset = out_offset;
     reduce_samples_tma_kernel<KT, MAXU, FUSE_E, SamplesExchange><<<grid, kThreads, smem, stream>>>(
-        Lp, sLi, sLt, X, ldx, T, dpad, k, TC, nstrips, stages, E, nullptr, ldo, flags, xch);
+        Lp, sLi, sLt, X, ldx, T, dpad, k, TC, nstrips, stages, E, nullptr, ldo, flags,
+        l2_resident_from_row(T, dpad), xch);
     CDR_RETURN_IF_LAUNCH_FAILED();
     return 0;
 }
@@ -795,7 +821,8 @@ static int launch_features_strip(const double* M, long ldm, const double* X, lon
     if (rc) return rc;
     const int grid = nstrips < sm_count() ? nstrips : sm_count();
     reduce_features_strip_kernel<KT, MAXUQ><<<grid, kThreads, smem, stream>>>(
-        M, ldm, X, ldx, T, dpad, k, TC, nstrips, stages, (double*)workspace, flags, gram);
+        M, ldm, X, ldx, T, dpad, k, TC, nstrips, stages, (double*)workspace, flags, gram,
+        l2_resident_from_row(T, dpad));
     CDR_RETURN_IF_LAUNCH_FAILED();
     if (out == nullptr) return 0;          // the caller consumes the per-strip partials itself
     const long nitems = (long)T * (KP / 2);

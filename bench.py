@@ -568,13 +568,13 @@ def kmeans_block(args, hbm_peak, peak_src):
         'metric': 'kmeans_lloyd_iterations_per_sec_jra55', 'value': 1e3 / ms_iter,
         'unit': 'iterations/s', 'ms_per_lloyd_iteration': ms_iter, 'n_iter': int(n_iter),
         'device_loop': stats['device_loop'], 'fit_loop_ms': stats['loop_ms'],
-        'timed': '200 graph-replayed Lloyd iterations (5 kernels each), CUDA events',
+        'timed': '200 graph-replayed Lloyd iterations (4 kernels each), CUDA events',
         'roofline': {'bound': 'hbm', 'kernel': 'the two streaming passes of a Lloyd iteration',
                      'algorithmic_bytes_per_iteration': 2 * pass_bytes,
                      'achieved': 2 * pass_bytes / (ms_iter * 1e-3) / 1e9, 'peak': hbm_peak,
                      'unit': 'GB/s', 'frac': 2 * pass_bytes / (ms_iter * 1e-3) / 1e9 / hbm_peak,
                      'peak_source': peak_src,
-                     'note': 'whole iteration (5 kernels incl. assignment and centre update); '
+                     'note': 'whole iteration (4 kernels: two streaming passes, assignment, centre update); '
                              'X (234 MB) is larger than the L2'},
         'e2e': {'value': n_iter / fit_s, 'unit': 'iterations/s', 'fit_seconds': fit_s,
                 'h2d_bytes_per_step': X.nbytes / max(n_iter, 1),

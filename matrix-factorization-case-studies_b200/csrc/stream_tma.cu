@@ -619,7 +619,8 @@ constexpr size_t kSmemBudget = 220 * 1024;
 // re-read before it is evicted anyway, so it should not displace the partials and the small
 // replicated matrices -- makes the passes 2-8 % faster (100 / 102 -> 98 / 94 us); an
 // evict_last band of 48-112 MB brought no L2 hits on top of that, so the default band is
-// empty.  CDR_L2_RESIDENT_MB sets a band size for experiments.
+// empty.  CDR_L2_RESIDENT_MB sets a band size for experiments.  A matrix of at most 96 MB is
+// marked evict_last as a whole.
 static int l2_resident_from_row(int T, int dpad)
 {
     static long band_bytes = -1;
@@ -627,6 +628,9 @@ static int l2_resident_from_row(int T, int dpad)
         const char* e = getenv("CDR_L2_RESIDENT_MB");
         band_bytes = (e != nullptr ? atol(e) : 0L) * 1000000L;
     }
+    // a matrix that fits the L2 as a whole (a shard of a sample-sharded fit: 203 x 44 000 =
+    // 71 MB) is kept resident entirely
+    if ((long)T * dpad * 8 <= 96L * 1000000L) return 0;
     const long rows = band_bytes / ((long)dpad * 8);
     return rows >= T ? 0 : T - (int)rows;
 }

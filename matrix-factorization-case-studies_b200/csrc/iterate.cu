@@ -39,12 +39,37 @@ struct GpnhFusedArgs {
     cdr_peer_group g;        // world == 1: single GPU
 };
 
+#ifdef CDR_PROFILE_PHASES
+// profiling build only (profiles/phase_profile.py): per-warp time stamps of the phases
+__device__ unsigned long long cdr_phase_ns[8 * 4096];
+__device__ __forceinline__ unsigned long long phase_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define CDR_PHASE(slot)                                                                         \
+    do {                                                                                        \
+        if ((threadIdx.x & 31) == 0)                                                            \
+            cdr_phase_ns[(slot) * 4096 + blockIdx.x * kFusedWarps + (threadIdx.x >> 5)] = phase_now(); \
+    } while (0)
+#define CDR_TAIL_MARK(m)                                                                        \
+    do {                                                                                        \
+        __syncthreads();                                                                        \
+        if (threadIdx.x == 0) cdr_phase_ns[4 * 4096 + 4000 + (m)] = phase_now();                 \
+    } while (0)
+#else
+#define CDR_PHASE(slot)
+#define CDR_TAIL_MARK(m)
+#endif
+
 template <int KPL>
 __global__ void __launch_bounds__(kFusedThreads)
 gpnh_weights_fused_kernel(GpnhFusedArgs a)
 {
     cdr_loop_state* st = a.state;
     if (is_done(st)) return;
+    CDR_PHASE(0);
     constexpr int KP = 8 * KPL;
     constexpr int NST = KP * KP + 2;
     extern __shared__ double fsm[];
@@ -108,9 +133,17 @@ gpnh_weights_fused_kernel(GpnhFusedArgs a)
         }
     }
     tr_old = group8_sum(tr_old);
+    CDR_PHASE(1);
 
     int n_iter = 0, n_feval = 0;
     qp_solve<KPL>(As, arow, z0, b, present, a.p, has_sample, g, spw, x, n_iter, n_feval);
+    CDR_PHASE(2);
+#ifdef CDR_PROFILE_PHASES
+    if (lane == 0) {
+        cdr_phase_ns[6 * 4096 + blockIdx.x * kFusedWarps + warp] = (unsigned long long)n_iter;
+        cdr_phase_ns[7 * 4096 + blockIdx.x * kFusedWarps + warp] = (unsigned long long)n_feval;
+    }
+#endif
 
     double tr_new = 0.0;
     if (valid) {
@@ -124,9 +157,15 @@ gpnh_weights_fused_kernel(GpnhFusedArgs a)
     tr_new = group8_sum(tr_new);
 
     if (!fused_sample_statistics<KPL>(x, present, valid, k, tr_old, tr_new, wsum, a.cta_part,
-                                      &st->tickets[1]))
+                                      &st->tickets[1])) {
+        CDR_PHASE(3);
         return;
+    }
+    CDR_PHASE(3);
+    CDR_TAIL_MARK(0);
     fused_final_sum<KPL>(a.cta_part, fin);
+    CDR_PHASE(4);
+    CDR_TAIL_MARK(1);
     // sample-sharded fit: the statistics of all ranks, summed in rank order on every rank
     if (a.g.world > 1) peer::cta_allreduce_small(a.g, fin, NST);
     // fin[i * KP + j] = (Z'Z)[i][j] of the new weights; fin[KP*KP], fin[KP*KP+1] the traces
@@ -164,6 +203,7 @@ gpnh_weights_fused_kernel(GpnhFusedArgs a)
         }
     }
     __syncthreads();
+    CDR_TAIL_MARK(2);
     for (int idx = threadIdx.x; idx < k * k; idx += blockDim.x)
         a.ZtZ[idx] = fin[(idx / k) * KP + idx % k];
     if (*((volatile int*)&st->done)) return;          // CTA-uniform
@@ -175,9 +215,21 @@ gpnh_weights_fused_kernel(GpnhFusedArgs a)
             S[idx] = fin[(idx / k) * KP + idx % k];
         __syncthreads();
         const double pref = (k > 1) ? 4.0 / ((double)a.d * k * (k - 1)) : 0.0;
+        CDR_TAIL_MARK(3);
         solve_matrix_cta(S, k, kFusedMaxK, 1.0 / (double)a.T_total, a.lambda_W, pref, a.P, jac);
     }
+    CDR_TAIL_MARK(4);
+    CDR_PHASE(5);
 }
+
+#ifdef CDR_PROFILE_PHASES
+}  // namespace cdr
+extern "C" int cdr_debug_phase_read(unsigned long long* out)
+{
+    return (int)cudaMemcpyFromSymbol(out, cdr::cdr_phase_ns, sizeof(unsigned long long) * 8 * 4096);
+}
+namespace cdr {
+#endif
 
 static size_t fused_smem_bytes(int kp)
 {

@@ -53,11 +53,27 @@ __device__ __forceinline__ double aa_grad_entry16(const cdr_aa_buffers& b, const
     return b.grad_scale * (s - b.alpha[j] * kz);
 }
 
+#ifdef CDR_PROFILE_PHASES
+// profiling build only (profiles/phase_profile.py)
+__device__ unsigned long long cdr_head_ns[16 * 16];
+#define CDR_HEAD_MARK(m)                                                                  \
+    do {                                                                                  \
+        if (threadIdx.x == 0) {                                                           \
+            unsigned long long t__;                                                       \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                       \
+            cdr_head_ns[blockIdx.x * 16 + (m)] = t__;                                     \
+        }                                                                                 \
+    } while (0)
+#else
+#define CDR_HEAD_MARK(m)
+#endif
+
 // ---------------------------------------------------------------------- kernel 1
 __global__ void __launch_bounds__(1024) aa_head_kernel(cdr_aa_buffers b, cdr_spg_params p)
 {
     cdr_loop_state* st = b.state;
     if (is_done(st)) return;
+    CDR_HEAD_MARK(0);
     extern __shared__ double sm[];
     double* scratch = sm;
     double* coef = sm + 64;
@@ -73,7 +89,9 @@ __global__ void __launch_bounds__(1024) aa_head_kernel(cdr_aa_buffers b, cdr_spg
     for (int i = threadIdx.x; i < kFusedMaxK; i += blockDim.x)
         coef[i] = (i < k) ? b.alpha[j] * b.alpha[i] * b.ZtZ[j * k + i] : 0.0;
     __syncthreads();
+    CDR_HEAD_MARK(1);
     double th = block_simplex_threshold(work, 1, T, scratch);
+    CDR_HEAD_MARK(2);
     double a0[1] = {0.0};
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
         const double x = fmax(work[t] - th, 0.0);
@@ -82,6 +100,7 @@ __global__ void __launch_bounds__(1024) aa_head_kernel(cdr_aa_buffers b, cdr_spg
     }
     block_sum<1>(a0, scratch);
     if (threadIdx.x == 0) b.row_scratch[RS_A0 * k + j] = b.alpha[j] * a0[0];
+    CDR_HEAD_MARK(3);
 
     // g = df(x) (spg.py:176); work = x - g
     for (int t = threadIdx.x; t < T; t += 2 * blockDim.x) {
@@ -98,7 +117,9 @@ __global__ void __launch_bounds__(1024) aa_head_kernel(cdr_aa_buffers b, cdr_spg
     const bool explicit_alpha = p.alpha0 > 0.0;        // spg.py:151; used unclamped when given
     if (!explicit_alpha) {
         __syncthreads();
+        CDR_HEAD_MARK(4);
         th = block_simplex_threshold(work, 1, T, scratch);
+        CDR_HEAD_MARK(5);
         double m = 0.0;
         for (int t = threadIdx.x; t < T; t += blockDim.x)
             m = fmax(m, fabs(fmax(work[t] - th, 0.0) - crow[t]));
@@ -109,6 +130,7 @@ __global__ void __launch_bounds__(1024) aa_head_kernel(cdr_aa_buffers b, cdr_spg
     // ---- barrier over the k row CTAs (all resident: k <= 16).  The counter only grows:
     // every launch adds exactly k, so the k arrivals of this launch see old values in
     // [n k, (n + 1) k) and wait for (n + 1) k.
+    CDR_HEAD_MARK(6);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -120,6 +142,7 @@ __global__ void __launch_bounds__(1024) aa_head_kernel(cdr_aa_buffers b, cdr_spg
     }
     __syncthreads();
 
+    CDR_HEAD_MARK(7);
     // first step length (spg.py:178-189)
     double alpha;
     if (explicit_alpha) {
@@ -137,7 +160,9 @@ __global__ void __launch_bounds__(1024) aa_head_kernel(cdr_aa_buffers b, cdr_spg
     // d = P(x - alpha g) - x with <d,g>, <d,d> and the linear term along d (spg.py:191-206)
     for (int t = threadIdx.x; t < T; t += blockDim.x) work[t] = crow[t] - alpha * grow[t];
     __syncthreads();
+    CDR_HEAD_MARK(8);
     th = block_simplex_threshold(work, 1, T, scratch);
+    CDR_HEAD_MARK(9);
     double r[3] = {0.0, 0.0, 0.0};
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
         const double d = fmax(work[t] - th, 0.0) - crow[t];
@@ -152,7 +177,17 @@ __global__ void __launch_bounds__(1024) aa_head_kernel(cdr_aa_buffers b, cdr_spg
         b.row_scratch[RS_DD * k + j] = r[1];
         b.row_scratch[RS_A1 * k + j] = b.alpha[j] * r[2];
     }
+    CDR_HEAD_MARK(10);
 }
+
+#ifdef CDR_PROFILE_PHASES
+}  // namespace cdr
+extern "C" int cdr_debug_head_read(unsigned long long* out)
+{
+    return (int)cudaMemcpyFromSymbol(out, cdr::cdr_head_ns, sizeof(unsigned long long) * 16 * 16);
+}
+namespace cdr {
+#endif
 
 // ---------------------------------------------------------------------- kernel 4
 constexpr int kFinTB = 32;             // samples per CTA

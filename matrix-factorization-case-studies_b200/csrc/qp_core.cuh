@@ -94,6 +94,12 @@ __device__ __forceinline__ void qp_solve(const double* As, const double (&arow)[
     int n_feval = 1;
     int n_iter = 0;
     double alpha_s = 1.0;
+    // bracket of epsilon_two^2 for the convergence test (a tiny epsilon_two whose square
+    // underflows always takes the square root)
+    const double eps2_sq = p.epsilon_two > 0.0 ? p.epsilon_two * p.epsilon_two : 0.0;
+    const bool eps2_ok = eps2_sq > 1e-290;
+    const double eps2_lo = eps2_ok ? eps2_sq * (1.0 - 1e-12) : 0.0;
+    const double eps2_hi = eps2_ok ? eps2_sq * (1.0 + 1e-12) : (p.epsilon_two > 0.0 ? INFINITY : 0.0);
     bool active = valid;     // group-uniform
 
     for (int it = 0; it < p.max_iterations; ++it) {
@@ -133,15 +139,19 @@ __device__ __forceinline__ void qp_solve(const double* As, const double (&arow)[
         const double delta = group8_sum(sd);
         const double dkdk = group8_sum(sdd);
 
-        // ---- non-monotone reference value (spg.py:343-347)
+        // ---- non-monotone reference value (spg.py:343-347); memory = 1 (the default of
+        // quad_simplex_spg) is the monotone search on f_old alone
+        double f_max = f_old;
+        if (p.memory > 1) {
 #pragma unroll
-        for (int i = CDR_MAX_MEMORY - 1; i > 0; --i)
-            if (i < p.memory) f_mem[i] = f_mem[i - 1];
-        f_mem[0] = f_old;
-        double f_max = -INFINITY;
+            for (int i = CDR_MAX_MEMORY - 1; i > 0; --i)
+                if (i < p.memory) f_mem[i] = f_mem[i - 1];
+            f_mem[0] = f_old;
+            f_max = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < CDR_MAX_MEMORY; ++i)
-            if (i < p.memory && !isnan(f_mem[i])) f_max = fmax(f_max, f_mem[i]);
+            for (int i = 0; i < CDR_MAX_MEMORY; ++i)
+                if (i < p.memory && !isnan(f_mem[i])) f_max = fmax(f_max, f_mem[i]);
+        }
 
         // ---- line search (spg.py:349-372).  Trial points are x_old + lam d; A x is linear
         // in lam, so one extra mat-vec A d makes every backtracking trial a reduction only.
@@ -207,9 +217,12 @@ __device__ __forceinline__ void qp_solve(const double* As, const double (&arow)[
                 if (j < nvalid && ends) stop = first + j;
             }
             // earliest such trial over the replicas of the sample
+            // (a fixed four shuffles: with fewer replicas some of them are read twice)
             int m = stop;
-            for (int rho = 0; rho < replicas; ++rho)
-                m = min(m, __shfl_sync(CDR_FULL_MASK, stop, (sample_group + spw * rho) * 8 + g));
+#pragma unroll
+            for (int rho = 0; rho < 4; ++rho)
+                m = min(m, __shfl_sync(CDR_FULL_MASK, stop,
+                                       (sample_group + spw * (rho & (replicas - 1))) * 8 + g));
             const int round_trials = halving ? 4 * replicas : 1;
             const int last = (m == 99) ? round_trials - 1 : m;   // the trial the search is at now
             const int jsel = last & 3;
@@ -251,15 +264,17 @@ __device__ __forceinline__ void qp_solve(const double* As, const double (&arow)[
 
         // ---- projected-gradient residual (spg.py:388-394)
         group8_project<KPL>(tmp, prj);
-        double r2 = 0.0, rinf = 0.0;
+        double r2 = 0.0;
+        bool below = true;           // max |res| < epsilon_one  <=>  every |res| is
 #pragma unroll
         for (int r = 0; r < KPL; ++r) {
             const double res = prj[r] - xn[r];
             r2 += res * res;
-            rinf = fmax(rinf, fabs(res));
+            below = below && (fabs(res) < p.epsilon_one);
         }
         r2 = group8_sum(r2);
-        rinf = group8_max(rinf);
+        const bool rinf_small =
+            ((__ballot_sync(CDR_FULL_MASK, below) >> ((threadIdx.x & 24u))) & 0xffu) == 0xffu;
 
         if (active) {
 #pragma unroll
@@ -271,7 +286,11 @@ __device__ __forceinline__ void qp_solve(const double* As, const double (&arow)[
             f_old = f_new;                     // spg.py:386 re-evaluates the same expression
             n_feval += fe + 1;
             n_iter = it;
-            const bool conv = (sqrt(r2) < p.epsilon_two) || (rinf < p.epsilon_one);
+            // sqrt(r2) < epsilon_two, with the square root taken only when r2 is within
+            // rounding distance of epsilon_two^2
+            bool r2_small = r2 < eps2_lo;
+            if (!r2_small && r2 < eps2_hi) r2_small = sqrt(r2) < p.epsilon_two;
+            const bool conv = r2_small || rinf_small;
             if (conv || n_feval > p.max_feval) active = false;
         }
     }

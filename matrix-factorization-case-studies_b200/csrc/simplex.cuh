@@ -54,24 +54,59 @@ __device__ __forceinline__ double block_simplex_threshold(const double* work, lo
     return t;
 }
 
-// Threshold for one vector of <= 8 values spread over an aligned group of 8
-// lanes (one value per lane, absent components = -inf).  Uses
-// t = max_i (sum_{v_j >= v_i} v_j - 1) / #{v_j >= v_i}.  All lanes of the warp
-// must call this together.
+// {RN(1 / n), -n} for n = 0..8: operands of div_small_int
+static __device__ double2 kSmallDiv[9] = {{0.0, -0.0},      {1.0, -1.0},       {0.5, -2.0},
+                                           {1.0 / 3.0, -3.0}, {0.25, -4.0},      {0.2, -5.0},
+                                           {1.0 / 6.0, -6.0}, {1.0 / 7.0, -7.0}, {0.125, -8.0}};
+
+// a / n for an integer 1 <= n <= 8, correctly rounded, i.e. the same double as the IEEE
+// division (which costs ~40 dependent instructions here): with y = RN(1 / n), q0 = RN(a y) is
+// within one ulp of a / n, the residual a - n q0 is exact in one FMA, and RN(q0 + r y) is
+// RN(a / n) (Markstein's theorem; compared with a / n on 6.4e8 random operands).
+__device__ __forceinline__ double div_small_int(double a, int n)
+{
+    const double2 c = kSmallDiv[n];
+    const double q0 = a * c.x;
+    const double r = fma(c.y, q0, a);
+    return fma(r, c.x, q0);
+}
+
+// Threshold for one vector of <= 8 values spread over an aligned group of 8 lanes (one value
+// per lane, absent components = -inf), as simplex_projection.py:13-27 defines it: with the
+// values sorted in decreasing order, t = (sum of the rho largest - 1) / rho for the largest
+// rho whose smallest member is still above that quotient.  Lane i forms the candidate
+// c_i = (sum of the values >= v_i  -  1) / #{values >= v_i}; the lanes with v_i > c_i are the
+// support, rho is their number (one ballot) and t is the candidate of a lane of rank rho.
+// Near ties rounding can make the lanes' tests inconsistent (no lane of rank rho in the
+// support): then t = max_i c_i, which is the same number in exact arithmetic.
+// All lanes of the warp must call this together.
 __device__ __forceinline__ double group8_simplex_threshold(double v)
 {
-    double s = 0.0, n = 0.0;
+    // sum and number of the values >= v (pairwise sum: three dependent additions)
+    double term[8];
+    int n = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const double vj = __shfl_sync(CDR_FULL_MASK, v, j, 8);
-        if (vj >= v) {
-            s += vj;
-            n += 1.0;
-        }
+        const bool ge = vj >= v;
+        term[j] = ge ? vj : 0.0;
+        n += ge ? 1 : 0;
     }
-    double t = (s - 1.0) / n;          // -inf on absent lanes
+    const double s = ((term[0] + term[1]) + (term[2] + term[3])) +
+                     ((term[4] + term[5]) + (term[6] + term[7]));
+    const double c = div_small_int(s - 1.0, n);          // NaN on absent lanes
+    const bool in = v > c;
+    const unsigned shift = threadIdx.x & 24u;
+    const unsigned support = (__ballot_sync(CDR_FULL_MASK, in) >> shift) & 0xffu;
+    const int rho = __popc(support);
+    const unsigned owners = (__ballot_sync(CDR_FULL_MASK, in && n == rho) >> shift) & 0xffu;
+    double t = __shfl_sync(CDR_FULL_MASK, c, (int)shift + __ffs((int)owners) - 1);
+    if (__any_sync(CDR_FULL_MASK, owners == 0u)) {
+        double m = in ? c : ((v > -INFINITY && c == c) ? c : -INFINITY);
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(CDR_FULL_MASK, t, o, 8));
+        for (int o = 4; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(CDR_FULL_MASK, m, o, 8));
+        if (owners == 0u) t = m;
+    }
     return t;
 }
 
@@ -121,7 +156,10 @@ __device__ __forceinline__ void group8_project(const double (&v)[KPL], double (&
         t = group8_simplex_threshold_multi<KPL>(v);
     }
 #pragma unroll
-    for (int r = 0; r < KPL; ++r) out[r] = fmax(v[r] - t, 0.0);
+    for (int r = 0; r < KPL; ++r) {
+        const double d = v[r] - t;
+        out[r] = d > 0.0 ? d : 0.0;
+    }
 }
 
 }  // namespace cdr

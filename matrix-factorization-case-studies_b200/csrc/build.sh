@@ -1,6 +1,6 @@
 #!/bin/bash
 # Builds libcdr_b200.so (sm_100a only) next to the Python package.
-set -e
+set -eo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 OUT="$HERE/../convex_dim_red/libcdr_b200.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"

@@ -93,6 +93,23 @@ __device__ __forceinline__ int warp_sum_int(int v)
     return v;
 }
 
+// Second stage of the block reductions for eight warps (256 threads): every aligned group of
+// eight lanes combines the eight warp results in three butterfly steps.  The full five-step
+// butterfly over lanes padded with the neutral element forms the same tree, so the results
+// are identical.
+__device__ __forceinline__ double group8_tree_sum(double x)
+{
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) x += __shfl_xor_sync(CDR_FULL_MASK, x, o);
+    return x;
+}
+__device__ __forceinline__ double group8_tree_max(double x)
+{
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(CDR_FULL_MASK, x, o));
+    return x;
+}
+
 // Block-wide sum of up to N values per thread.  `scratch` must hold
 // N * 32 doubles.  All threads receive the result.  blockDim.x must be a
 // multiple of 32 and <= 1024.
@@ -109,11 +126,39 @@ __device__ __forceinline__ void block_sum(double (&v)[N], double* scratch)
         for (int i = 0; i < N; ++i) scratch[i * 32 + warp] = v[i];
     }
     __syncthreads();
+    if (nwarps == 8) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = group8_tree_sum(scratch[i * 32 + (lane & 7)]);
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         double x = (lane < nwarps) ? scratch[i * 32 + lane] : 0.0;
         v[i] = warp_sum(x);
     }
+}
+
+// sum and maximum in one exchange (scratch: 64 doubles); same results as block_sum<1> and
+// block_max
+__device__ __forceinline__ void block_sum_and_max(double& sum, double& mx, double* scratch)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    sum = warp_sum(sum);
+    mx = warp_max(mx);
+    __syncthreads();                      // scratch may still be read from a previous call
+    if (lane == 0) {
+        scratch[warp] = sum;
+        scratch[32 + warp] = mx;
+    }
+    __syncthreads();
+    if (nwarps == 8) {
+        sum = group8_tree_sum(scratch[lane & 7]);
+        mx = group8_tree_max(scratch[32 + (lane & 7)]);
+        return;
+    }
+    sum = warp_sum((lane < nwarps) ? scratch[lane] : 0.0);
+    mx = warp_max((lane < nwarps) ? scratch[32 + lane] : -INFINITY);
 }
 
 __device__ __forceinline__ double block_max(double v, double* scratch)
@@ -124,6 +169,7 @@ __device__ __forceinline__ double block_max(double v, double* scratch)
     __syncthreads();
     if (lane == 0) scratch[warp] = v;
     __syncthreads();
+    if (nwarps == 8) return group8_tree_max(scratch[lane & 7]);
     double x = (lane < nwarps) ? scratch[lane] : -INFINITY;
     return warp_max(x);
 }

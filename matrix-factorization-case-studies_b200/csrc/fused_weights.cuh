@@ -123,8 +123,28 @@ __device__ __forceinline__ bool fused_sample_statistics(const double (&x)[KPL],
     return last;
 }
 
+// fixed-order sum of n values spaced `stride` doubles apart, 32 loads in flight (the tail of
+// the last batch reads nothing and adds zeros)
+__device__ __forceinline__ double strided_sum_cg32(const double* base, long stride, int n)
+{
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (int i = 0; i < n; i += 32) {
+        double v[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = (i + q < n) ? __ldcg(base + (long)(i + q) * stride) : 0.0;
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+            a0 += v[q];
+            a1 += v[q + 1];
+            a2 += v[q + 2];
+            a3 += v[q + 3];
+        }
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+
 // Last CTA: fin[0..NST) = sum over the CTAs of the grid of cta_part, fixed order.
-// fin: 4 * NST doubles of shared memory.  All threads of the CTA must call this.
+// fin: fused_fin_doubles(NST) doubles of shared memory.  All threads of the CTA must call this.
 template <int KPL>
 __device__ __forceinline__ void fused_final_sum(const double* cta_part, double* fin)
 {
@@ -136,11 +156,11 @@ __device__ __forceinline__ void fused_final_sum(const double* cta_part, double* 
     if (PH > 1) {
         const int e = (int)threadIdx.x % NST, ph = (int)threadIdx.x / NST;
         if (ph < PH)
-            phs[ph * NST + e] = strided_sum_cg(cta_part + (long)ph * NST + e, (long)PH * NST,
-                                               (nblk - ph + PH - 1) / PH);
+            phs[ph * NST + e] = strided_sum_cg32(cta_part + (long)ph * NST + e, (long)PH * NST,
+                                                 (nblk - ph + PH - 1) / PH);
     } else {
         for (int e = threadIdx.x; e < NST; e += blockDim.x)
-            phs[e] = strided_sum_cg(cta_part + e, NST, nblk);
+            phs[e] = strided_sum_cg32(cta_part + e, NST, nblk);
     }
     __syncthreads();
     for (int e = threadIdx.x; e < NST; e += blockDim.x) {
@@ -151,6 +171,8 @@ __device__ __forceinline__ void fused_final_sum(const double* cta_part, double* 
     }
     __syncthreads();
 }
+// doubles of shared memory behind `fin` for a statistics vector of nst entries
+static inline size_t fused_fin_doubles(int nst) { return (size_t)4 * nst; }
 
 template <auto Kern>
 static int ensure_dyn_smem(size_t smem)

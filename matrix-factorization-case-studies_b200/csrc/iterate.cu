@@ -75,7 +75,7 @@ gpnh_weights_fused_kernel(GpnhFusedArgs a)
     extern __shared__ double fsm[];
     double* As = fsm;                               // KP x KP (KPL > 1)
     double* wsum = fsm + (KPL > 1 ? KP * KP : 0);   // [kFusedWarps][NST]
-    double* fin = wsum + kFusedWarps * NST;         // NST (+ phases), then Jacobi scratch
+    double* fin = wsum + kFusedWarps * NST;         // NST + per-warp sums, then Jacobi scratch
     const int k = a.k, T = a.T;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane & 7, q = lane >> 3;
@@ -209,7 +209,7 @@ gpnh_weights_fused_kernel(GpnhFusedArgs a)
     if (*((volatile int*)&st->done)) return;          // CTA-uniform
     // solve matrix of the next dictionary step (gpnh_convex_coding.py:221-226)
     {
-        double* jac = fin + NST * 4;
+        double* jac = fin + 4 * NST;
         double* S = jac + 2 * kFusedMaxK * kJacLd;     // dense k x k copy
         for (int idx = threadIdx.x; idx < k * k; idx += blockDim.x)
             S[idx] = fin[(idx / k) * KP + idx % k];
@@ -234,7 +234,7 @@ namespace cdr {
 static size_t fused_smem_bytes(int kp)
 {
     const int nst = kp * kp + 2;
-    return ((kp > 8 ? (size_t)kp * kp : 0) + (size_t)kFusedWarps * nst + (size_t)nst * 4 +
+    return ((kp > 8 ? (size_t)kp * kp : 0) + (size_t)kFusedWarps * nst + fused_fin_doubles(nst) +
             2 * (size_t)kFusedMaxK * kJacLd + (size_t)kFusedMaxK * kFusedMaxK) * sizeof(double);
 }
 

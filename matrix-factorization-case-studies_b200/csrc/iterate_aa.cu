@@ -36,21 +36,43 @@ namespace cdr {
 enum { RS_A0 = 0, RS_ROWMAX = 1, RS_DELTA = 2, RS_DD = 3, RS_A1 = 4, RS_BETA = 5, RS_R2 = 6, RS_RINF = 7 };
 
 constexpr int kAaRowMaxT = 26000;      // aa_steps.cu: rows are staged in shared memory
+constexpr int kAaStagedMaxT = 6000;    // head kernel: four row buffers of T doubles (<= 188 KB)
 
-// gradient entry (j, t):  s_g * (sum_i a_j a_i ZtZ[j][i] CK[i][t] - a_j KZt[j][t]), k <= 16.
-// The k loads of the column are issued together (a loop with a run-time trip count would
-// serialise one L2 round trip per component); coef[i] = 0 for i >= k, and adding 0 * 0 leaves
-// the sum -- formed in the order i = 0, 1, ... as in aa_steps.cu -- unchanged.
-__device__ __forceinline__ double aa_grad_entry16(const cdr_aa_buffers& b, const double* coef, int j, int t)
+// gradient entry (j, t):  s_g * (sum_i a_j a_i ZtZ[j][i] CK[i][t] - a_j KZt[j][t]), k <= 16;
+// coef[i] = a_j a_i ZtZ[j][i], 0 for i >= k (adding 0 * 0 leaves the sum -- formed in the order
+// i = 0, 1, ... as in aa_steps.cu -- unchanged).  One expression for every kernel that forms the
+// gradient, so they all round alike.
+__device__ __forceinline__ double aa_grad_value(const double (&ck)[kFusedMaxK], const double* coef,
+                                                double alpha_j, double kz, double grad_scale)
 {
-    double ck[kFusedMaxK];
-#pragma unroll
-    for (int i = 0; i < kFusedMaxK; ++i) ck[i] = (i < b.k) ? b.CK[(long)i * b.ldt + t] : 0.0;
-    const double kz = b.KZt[(long)j * b.ldt + t];
     double s = 0.0;
 #pragma unroll
     for (int i = 0; i < kFusedMaxK; ++i) s = fma(coef[i], ck[i], s);
-    return b.grad_scale * (s - b.alpha[j] * kz);
+    return grad_scale * (s - alpha_j * kz);
+}
+
+// The k loads of the column are issued together (a loop with a run-time trip count would
+// serialise one L2 round trip per component).
+__device__ __forceinline__ void aa_load_ck_column(const cdr_aa_buffers& b, int t, double (&ck)[kFusedMaxK])
+{
+#pragma unroll
+    for (int i = 0; i < kFusedMaxK; ++i) ck[i] = (i < b.k) ? b.CK[(long)i * b.ldt + t] : 0.0;
+}
+
+__device__ __forceinline__ double aa_grad_entry16(const cdr_aa_buffers& b, const double* coef, int j, int t)
+{
+    double ck[kFusedMaxK];
+    aa_load_ck_column(b, t, ck);
+    return aa_grad_value(ck, coef, b.alpha[j], b.KZt[(long)j * b.ldt + t], b.grad_scale);
+}
+
+// coef[j][i] of all rows (see aa_grad_value) into shared memory: KP x kFusedMaxK doubles
+__device__ __forceinline__ void aa_fill_coef(const cdr_aa_buffers& b, double* coef, int kp)
+{
+    for (int idx = threadIdx.x; idx < kp * kFusedMaxK; idx += blockDim.x) {
+        const int j = idx / kFusedMaxK, i = idx % kFusedMaxK;
+        coef[idx] = (j < b.k && i < b.k) ? b.alpha[j] * b.alpha[i] * b.ZtZ[j * b.k + i] : 0.0;
+    }
 }
 
 #ifdef CDR_PROFILE_PHASES
@@ -69,10 +91,15 @@ __device__ unsigned long long cdr_head_ns[16 * 16];
 #endif
 
 // ---------------------------------------------------------------------- kernel 1
-__global__ void __launch_bounds__(1024) aa_head_kernel(cdr_aa_buffers b, cdr_spg_params p)
+// grad_ready: G already holds df(x) (aa_kzt_gradient_kernel / aa_initial_gradient_kernel wrote it with
+// the (K Z)' it belongs to; the gradient uses the maintained C K, not the re-projected x).
+// staged: the row's x, g and (K Z)' are kept in shared memory next to `work` (4 T doubles);
+// otherwise -- long rows of a sample-sharded fit -- they are re-read from global memory.
+__global__ void __launch_bounds__(1024)
+aa_head_kernel(cdr_aa_buffers b, cdr_spg_params p, int grad_ready, int staged)
 {
     cdr_loop_state* st = b.state;
-    if (is_done(st)) return;
+    const int done = is_done(st) ? 1 : 0;
     CDR_HEAD_MARK(0);
     extern __shared__ double sm[];
     double* scratch = sm;
@@ -82,20 +109,58 @@ __global__ void __launch_bounds__(1024) aa_head_kernel(cdr_aa_buffers b, cdr_spg
     double* crow = b.C + (long)j * b.ldt;
     double* grow = b.G + (long)j * b.ldt;
     double* drow = b.D + (long)j * b.ldt;
-    const double* kz = b.KZt + (long)j * b.ldt;
+    const double* kzrow = b.KZt + (long)j * b.ldt;
+    // generic pointers: shared-memory copies when staged, the global rows otherwise
+    double* xs = staged ? work + T : crow;
+    double* gs = staged ? work + 2 * (long)T : grow;
+    const double* kz = staged ? work + 3 * (long)T : kzrow;
 
-    // x = project(x0) (spg.py:146-148) and the linear trace term a0 = a_j <x, (K Z)_j>
-    for (int t = threadIdx.x; t < T; t += blockDim.x) work[t] = crow[t];
-    for (int i = threadIdx.x; i < kFusedMaxK; i += blockDim.x)
-        coef[i] = (i < k) ? b.alpha[j] * b.alpha[i] * b.ZtZ[j * k + i] : 0.0;
+    // the loads below do not depend on `done` (issued together with its read); the three rows
+    // of a staged launch go out together, eight elements per thread before the first store
+    if (staged) {
+        double* xw = work;                              // known shared-memory pointers: the
+        double* gw = work + 2 * (long)T;                // loads can be hoisted over the stores
+        double* kw = work + 3 * (long)T;
+        const double* __restrict__ cg = crow;
+        const double* __restrict__ gg = grow;
+        const double* __restrict__ kg = kzrow;
+        for (int t0 = threadIdx.x; t0 < T; t0 += 8 * blockDim.x) {
+            double c[8], g[8], z[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int t = t0 + u * blockDim.x;
+                c[u] = (t < T) ? __ldcg(cg + t) : 0.0;
+                z[u] = (t < T) ? __ldcg(kg + t) : 0.0;
+                g[u] = (t < T && grad_ready) ? __ldcg(gg + t) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int t = t0 + u * blockDim.x;
+                if (t < T) {
+                    xw[t] = c[u];
+                    kw[t] = z[u];
+                    if (grad_ready) gw[t] = g[u];
+                }
+            }
+        }
+    } else {
+        for (int t = threadIdx.x; t < T; t += blockDim.x) work[t] = crow[t];
+    }
+    if (!grad_ready)
+        for (int i = threadIdx.x; i < kFusedMaxK; i += blockDim.x)
+            coef[i] = (i < k) ? b.alpha[j] * b.alpha[i] * b.ZtZ[j * k + i] : 0.0;
+    if (done) return;
     __syncthreads();
     CDR_HEAD_MARK(1);
+
+    // x = project(x0) (spg.py:146-148) and the linear trace term a0 = a_j <x, (K Z)_j>
     double th = block_simplex_threshold(work, 1, T, scratch);
     CDR_HEAD_MARK(2);
     double a0[1] = {0.0};
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
         const double x = fmax(work[t] - th, 0.0);
         crow[t] = x;
+        if (staged) xs[t] = x;
         a0[0] = fma(x, kz[t], a0[0]);
     }
     block_sum<1>(a0, scratch);
@@ -103,15 +168,22 @@ __global__ void __launch_bounds__(1024) aa_head_kernel(cdr_aa_buffers b, cdr_spg
     CDR_HEAD_MARK(3);
 
     // g = df(x) (spg.py:176); work = x - g
-    for (int t = threadIdx.x; t < T; t += 2 * blockDim.x) {
-        const int t2 = t + blockDim.x;
-        const double g = aa_grad_entry16(b, coef, j, t);
-        const double g2 = (t2 < T) ? aa_grad_entry16(b, coef, j, t2) : 0.0;
-        grow[t] = g;
-        work[t] = crow[t] - g;
-        if (t2 < T) {
-            grow[t2] = g2;
-            work[t2] = crow[t2] - g2;
+    if (grad_ready) {
+        // (each thread re-reads its own elements of xs / crow)
+        for (int t = threadIdx.x; t < T; t += blockDim.x) work[t] = xs[t] - gs[t];
+    } else {
+        for (int t = threadIdx.x; t < T; t += 2 * blockDim.x) {
+            const int t2 = t + blockDim.x;
+            const double g = aa_grad_entry16(b, coef, j, t);
+            const double g2 = (t2 < T) ? aa_grad_entry16(b, coef, j, t2) : 0.0;
+            grow[t] = g;
+            if (staged) gs[t] = g;
+            work[t] = xs[t] - g;
+            if (t2 < T) {
+                grow[t2] = g2;
+                if (staged) gs[t2] = g2;
+                work[t2] = xs[t2] - g2;
+            }
         }
     }
     const bool explicit_alpha = p.alpha0 > 0.0;        // spg.py:151; used unclamped when given
@@ -122,7 +194,7 @@ __global__ void __launch_bounds__(1024) aa_head_kernel(cdr_aa_buffers b, cdr_spg
         CDR_HEAD_MARK(5);
         double m = 0.0;
         for (int t = threadIdx.x; t < T; t += blockDim.x)
-            m = fmax(m, fabs(fmax(work[t] - th, 0.0) - crow[t]));
+            m = fmax(m, fabs(fmax(work[t] - th, 0.0) - xs[t]));
         m = block_max(m, scratch);
         if (threadIdx.x == 0) b.row_scratch[RS_ROWMAX * k + j] = m;
     }
@@ -158,16 +230,16 @@ __global__ void __launch_bounds__(1024) aa_head_kernel(cdr_aa_buffers b, cdr_spg
     }
 
     // d = P(x - alpha g) - x with <d,g>, <d,d> and the linear term along d (spg.py:191-206)
-    for (int t = threadIdx.x; t < T; t += blockDim.x) work[t] = crow[t] - alpha * grow[t];
+    for (int t = threadIdx.x; t < T; t += blockDim.x) work[t] = xs[t] - alpha * gs[t];
     __syncthreads();
     CDR_HEAD_MARK(8);
     th = block_simplex_threshold(work, 1, T, scratch);
     CDR_HEAD_MARK(9);
     double r[3] = {0.0, 0.0, 0.0};
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
-        const double d = fmax(work[t] - th, 0.0) - crow[t];
+        const double d = fmax(work[t] - th, 0.0) - xs[t];
         drow[t] = d;
-        r[0] = fma(d, grow[t], r[0]);
+        r[0] = fma(d, gs[t], r[0]);
         r[1] = fma(d, d, r[1]);
         r[2] = fma(d, kz[t], r[2]);
     }
@@ -543,6 +615,85 @@ __global__ void __launch_bounds__(kFusedThreads) aa_weights_fused_kernel(AaWeigh
         b.ZtZ[idx] = fin[(idx / k) * KP + idx % k];
 }
 
+// ---------------------------------------------------------------------- kernel 8
+// (K Z)'[j][t] = sum over strips of part[strip][t][j] -- the summation order of
+// reduce_features_strip_finalize_kernel -- and, while the column is at hand, the gradient of
+// the next dictionary step G[j][t] = df(x)[j][t] (archetypal_analysis.py:293-299): it needs
+// only this column of (K Z)' and of the maintained C K, the new Z'Z and the scale factors, all
+// final at this point, and saves the head kernel of the next iteration its (k + 1) k T loads.
+template <int KT>
+__global__ void __launch_bounds__(256)
+aa_kzt_gradient_kernel(const double* __restrict__ part, int nstrips, cdr_aa_buffers b)
+{
+    if (is_done(b.state)) return;
+    constexpr int KP = 8 * KT;
+    constexpr int PAIRS = KP / 2;
+    __shared__ double2 red[8][32];
+    __shared__ double coef[KP * kFusedMaxK];
+    const int k = b.k, T = b.T;
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const long item = (long)blockIdx.x * 32 + lane;
+    const long nitems = (long)T * PAIRS;
+    const long stride = nitems;
+    const int per = (nstrips + 7) / 8;
+    aa_fill_coef(b, coef, KP);
+    double s0 = 0.0, s1 = 0.0;
+    if (item < nitems) {
+        const double2* src = reinterpret_cast<const double2*>(part) + item;
+        const int hi = min(nstrips, (grp + 1) * per);
+        int sidx = grp * per;
+        for (; sidx + 2 <= hi; sidx += 2) {
+            const double2 v0 = src[(long)sidx * stride];
+            const double2 v1 = src[(long)(sidx + 1) * stride];
+            s0 += v0.x; s1 += v0.y;
+            s0 += v1.x; s1 += v1.y;
+        }
+        for (; sidx < hi; ++sidx) {
+            const double2 v = src[(long)sidx * stride];
+            s0 += v.x;
+            s1 += v.y;
+        }
+    }
+    red[grp][lane] = make_double2(s0, s1);
+    __syncthreads();
+    if (grp == 0 && item < nitems) {
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            a0 += red[q][lane].x;
+            a1 += red[q][lane].y;
+        }
+        const int t = (int)(item / PAIRS), j = 2 * (int)(item % PAIRS);
+        double ck[kFusedMaxK];
+        aa_load_ck_column(b, t, ck);
+        if (j < k) {
+            b.KZt[(long)j * b.ldt + t] = a0;
+            b.G[(long)j * b.ldt + t] = aa_grad_value(ck, coef + j * kFusedMaxK, b.alpha[j], a0, b.grad_scale);
+        }
+        if (j + 1 < k) {
+            b.KZt[(long)(j + 1) * b.ldt + t] = a1;
+            b.G[(long)(j + 1) * b.ldt + t] =
+                aa_grad_value(ck, coef + (j + 1) * kFusedMaxK, b.alpha[j + 1], a1, b.grad_scale);
+        }
+    }
+}
+
+// The gradient alone, from (K Z)' in memory (after cdr_aa_prepare_enqueue): one sample per thread.
+__global__ void __launch_bounds__(256) aa_initial_gradient_kernel(cdr_aa_buffers b)
+{
+    if (is_done(b.state)) return;
+    __shared__ double coef[kFusedMaxK * kFusedMaxK];
+    aa_fill_coef(b, coef, kFusedMaxK);
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= b.T) return;
+    double ck[kFusedMaxK];
+    aa_load_ck_column(b, t, ck);
+    for (int j = 0; j < b.k; ++j)
+        b.G[(long)j * b.ldt + t] = aa_grad_value(ck, coef + j * kFusedMaxK, b.alpha[j],
+                                                 b.KZt[(long)j * b.ldt + t], b.grad_scale);
+}
+
 // ---------------------------------------------------------------------- kernel 8 (sharded)
 // out[j][col0 + t] = sum over strips of part[strip][t][j] for the local samples t, written to
 // EVERY rank (the k x T matrix is replicated); the last CTA then meets the other ranks, after
@@ -610,7 +761,7 @@ features_finalize_push_kernel(const double* __restrict__ part, int Tl, int nstri
 static size_t aa_fused_smem_bytes(int kp)
 {
     const int nst = kp * kp + 2;
-    return ((kp > 8 ? (size_t)kp * kp : 0) + (size_t)kFusedWarps * nst + (size_t)nst * 4) * sizeof(double);
+    return ((kp > 8 ? (size_t)kp * kp : 0) + (size_t)kFusedWarps * nst + fused_fin_doubles(nst)) * sizeof(double);
 }
 
 static int aa_row_threads(int T)
@@ -753,6 +904,11 @@ extern "C" int cdr_aa_prepare_enqueue(const cdr_aa_problem* p, cdr_stream_t stre
     CDR_TRY(aa_apply_left(p, w, b.C, b.CK, s));
     ds[0] = kt_desc(b, b.CK, b.C, b.CKCt);
     CDR_TRY(cdr_small_gram(ds, 1, w.gram, w.gram_bytes, b.state, s));
+    // df(x) of the first dictionary step (the eight-kernel iteration expects it in G)
+    if (k <= kFusedMaxK) {
+        aa_initial_gradient_kernel<<<(b.T + 255) / 256, 256, 0, s>>>(b);
+        CDR_RETURN_IF_LAUNCH_FAILED();
+    }
     return cdr_loop_begin(b.state, s);
 }
 
@@ -803,10 +959,13 @@ extern "C" int cdr_aa_iterate_enqueue(const cdr_aa_problem* p, cdr_stream_t stre
 
     // 1. head: projection, gradient, first step length, direction
     {
-        // the rows of the (replicated) dictionary span all samples
-        const size_t smem = (64 + CDR_MAX_COMPONENTS + (size_t)b.T) * sizeof(double);
+        // the rows of the (replicated) dictionary span all samples; short rows keep x, g and
+        // (K Z)' in shared memory as well.  On one GPU the gradient was left in G by
+        // cdr_aa_prepare_enqueue / the previous iteration's last kernel.
+        const int staged = (b.T <= kAaStagedMaxT) ? 1 : 0;
+        const size_t smem = (64 + CDR_MAX_COMPONENTS + (size_t)(staged ? 4 : 1) * b.T) * sizeof(double);
         CDR_TRY(ensure_dyn_smem<aa_head_kernel>(smem));
-        aa_head_kernel<<<k, aa_row_threads(b.T), smem, s>>>(b, dp);
+        aa_head_kernel<<<k, aa_row_threads(b.T), smem, s>>>(b, dp, sharded ? 0 : 1, staged);
         CDR_RETURN_IF_LAUNCH_FAILED();
     }
     // 2. D X (summed over ranks in the kernel's epilogue when sharded)
@@ -864,8 +1023,20 @@ extern "C" int cdr_aa_iterate_enqueue(const cdr_aa_problem* p, cdr_stream_t stre
         }
         CDR_RETURN_IF_LAUNCH_FAILED();
     }
-    // 6.-8. (K Z)' for the next dictionary step
-    if (!sharded) return aa_apply_right(p, w, s);
+    // 6.-8. (K Z)' and the gradient for the next dictionary step
+    if (!sharded) {
+        CDR_TRY(cdr_reduce_samples(p->Z, 1, k, p->X, p->ldx, T, d, k, nullptr, p->tmp_kd, p->ldx,
+                                   w.stream, w.stream_bytes, b.state, s));
+        const int rc = run_reduce_features_tma(p->tmp_kd, p->ldx, p->X, p->ldx, T, d, k, nullptr, 0,
+                                               w.stream, w.stream_bytes, b.state, s, nullptr);
+        if (rc != 0) return rc == CDR_TMA_NOT_APPLICABLE ? CDR_ERR_UNSUPPORTED : rc;
+        const int kp = (k <= 8) ? 8 : 16;
+        const int blocks = (int)(((long)T * (kp / 2) + 31) / 32);
+        if (k <= 8) aa_kzt_gradient_kernel<1><<<blocks, 256, 0, s>>>(w.stream, nstrips, b);
+        else aa_kzt_gradient_kernel<2><<<blocks, 256, 0, s>>>(w.stream, nstrips, b);
+        CDR_RETURN_IF_LAUNCH_FAILED();
+        return 0;
+    }
     CDR_TRY(cdr_reduce_samples_allreduce(p->peers, p->Z, 1, k, p->X, p->ldx, T, p->T_min, d, k, nullptr,
                                          peer::region_offset(grp, p->tmp_kd), p->ldx, b.state, s));
     {

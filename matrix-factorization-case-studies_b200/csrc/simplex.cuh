@@ -30,8 +30,7 @@ __device__ __forceinline__ double block_simplex_threshold(const double* work, lo
         r[0] += v;
         mx = fmax(mx, v);
     }
-    block_sum<1>(r, scratch);
-    mx = block_max(mx, scratch);
+    block_sum_and_max(r[0], mx, scratch);
     double t = fmax((r[0] - 1.0) / (double)n, mx - 1.0);
     int count_prev = n;
     for (int it = 0; it < 4096; ++it) {

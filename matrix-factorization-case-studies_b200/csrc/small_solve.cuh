@@ -15,6 +15,54 @@ namespace cdr {
 // with rcond=None (gpnh_convex_coding.py:224).
 constexpr int kJacLd = CDR_MAX_COMPONENTS + 1;
 
+// In-place Gauss-Jordan inversion of the symmetric positive definite k x k matrix A (shared
+// memory, leading dimension kJacLd) by one warp: lane c keeps column c in registers, pivot p
+// is broadcast from lane p.  Writes scale * A^-1 to P (row-major k x k) and returns 1, or
+// returns 0 (P untouched) when a pivot is not above 1e-10 * max diag.  All 32 lanes call this.
+constexpr int CDR_MAX_GJ = 32;                   // k <= 32 on the fast path (one lane per column)
+template <int KMAX>
+__device__ __forceinline__ int spd_inverse_warp(const double* A, int k, double scale,
+                                                double* __restrict__ P)
+{
+    const int lane = threadIdx.x & 31;
+    if (k > KMAX) return 0;
+    double col[KMAX];
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) col[i] = (i < k && lane < k) ? A[i * kJacLd + lane] : 0.0;
+    double dmax = (lane < k) ? A[lane * kJacLd + lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(CDR_FULL_MASK, dmax, o));
+    const double thr = 1e-10 * dmax;
+    bool ok = dmax > 0.0;
+#pragma unroll
+    for (int p = 0; p < KMAX; ++p) {
+        if (p < k && ok) {                                       // warp-uniform
+            const double piv = __shfl_sync(CDR_FULL_MASK, col[p], p);
+            if (!(piv > thr)) {
+                ok = false;
+            } else {
+                const double inv = 1.0 / piv;
+                const double rp = (lane == p) ? inv : col[p] * inv;       // row p of the result
+#pragma unroll
+                for (int i = 0; i < KMAX; ++i) {
+                    if (i != p && i < k) {
+                        const double f = __shfl_sync(CDR_FULL_MASK, col[i], p);
+                        col[i] = (lane == p) ? -f * inv : fma(-f, rp, col[i]);
+                    }
+                }
+                col[p] = rp;
+            }
+        }
+    }
+    if (!ok) return 0;
+    if (lane < k) {
+#pragma unroll
+        for (int i = 0; i < KMAX; ++i)
+            if (i < k) P[i * k + lane] = col[i] * scale;
+    }
+    return 1;
+}
+
 // All threads of the CTA call this together (blockDim.x a multiple of 32); jac_sm holds
 // 2 * kmax * kJacLd doubles of shared memory, kmax >= k.  ZtZ may be global or shared.
 __device__ __forceinline__ void solve_matrix_cta(const double* ZtZ, int k, int kmax, double inv_n,
@@ -37,70 +85,86 @@ __device__ __forceinline__ void solve_matrix_cta(const double* ZtZ, int k, int k
         double v = ZtZ[idx] * inv_n;
         if (k > 1) v += lambda_W * gw_prefactor * ((i == j ? (double)k : 0.0) - 1.0);
         A[i * kJacLd + j] = v;
-        V[i * kJacLd + j] = v;            // Cholesky works in V; Jacobi re-initialises it
     }
     __syncthreads();
 
     // ---- fast path: the matrix is symmetric positive definite and reasonably conditioned
-    // (the usual case): P = A^-1 by Cholesky, a few microseconds instead of ~50 for the
-    // Jacobi sweeps.  Any pivot below 1e-10 * max diag falls through to the
+    // (the usual case): P = A^-1 by Gauss-Jordan elimination without pivoting in one warp,
+    // about a microsecond instead of ~50 for the Jacobi sweeps.  The pivots are those of the
+    // Cholesky / LDL' factorisation; any of them below 1e-10 * max diag falls through to the
     // pseudo-inverse, which reproduces lstsq's minimum-norm solution for singular Z'Z.
-    if (tid < 32) {
-        const int lane = tid;
-        double dmax = 0.0;
-        for (int i = 0; i < k; ++i) dmax = fmax(dmax, V[i * kJacLd + i]);
-        const double thr = 1e-10 * dmax;
-        bool ok = dmax > 0.0;
-        for (int j = 0; j < k && ok; ++j) {
-            for (int i = j + lane; i < k; i += 32) {
-                double sacc = V[i * kJacLd + j];
-                for (int q = 0; q < j; ++q) sacc = fma(-V[i * kJacLd + q], V[j * kJacLd + q], sacc);
-                chol_tmp[i] = sacc;
-            }
-            __syncwarp();
-            const double dj = chol_tmp[j];
-            if (!(dj > thr)) {
-                ok = false;
-            } else {
-                const double root = sqrt(dj);
-                for (int i = j + lane; i < k; i += 32)
-                    V[i * kJacLd + j] = (i == j) ? root : chol_tmp[i] / root;
-            }
-            __syncwarp();
+    if (k <= CDR_MAX_GJ) {
+        if (tid < 32) {
+            int ok;
+            if (k <= 8) ok = spd_inverse_warp<8>(A, k, inv_n, P);
+            else if (k <= 16) ok = spd_inverse_warp<16>(A, k, inv_n, P);
+            else ok = spd_inverse_warp<CDR_MAX_GJ>(A, k, inv_n, P);
+            if (tid == 0) chol_ok = ok;
         }
-        if (ok) {
-            // columns of L^-1 by forward substitution (one column per lane), stored in A's
-            // upper part is not safe (A may still be needed) -> reuse chol-free rows of V:
-            // L^-1 overwrites the strictly-upper triangle + a separate diagonal pass
-            for (int c = lane; c < k; c += 32) {
-                // y = L^-1 e_c, kept in the upper triangle V[c][i] (i >= c)
-                double ycc = 1.0 / V[c * kJacLd + c];
-                for (int i = c + 1; i < k; ++i) {
-                    double sacc = V[i * kJacLd + c] * ycc;
-                    for (int q = c + 1; q < i; ++q) sacc = fma(V[i * kJacLd + q], V[c * kJacLd + q], sacc);
-                    V[c * kJacLd + i] = -sacc / V[i * kJacLd + i];
+        __syncthreads();
+        if (chol_ok) return;                      // CTA-uniform
+    } else {
+        // wider matrices: Cholesky in shared memory (V), same pivot test
+        for (int idx = tid; idx < k * k; idx += blockDim.x)
+            V[(idx / k) * kJacLd + idx % k] = A[(idx / k) * kJacLd + idx % k];
+        __syncthreads();
+        if (tid < 32) {
+            const int lane = tid;
+            double dmax = 0.0;
+            for (int i = 0; i < k; ++i) dmax = fmax(dmax, V[i * kJacLd + i]);
+            const double thr = 1e-10 * dmax;
+            bool ok = dmax > 0.0;
+            for (int j = 0; j < k && ok; ++j) {
+                for (int i = j + lane; i < k; i += 32) {
+                    double sacc = V[i * kJacLd + j];
+                    for (int q = 0; q < j; ++q) sacc = fma(-V[i * kJacLd + q], V[j * kJacLd + q], sacc);
+                    chol_tmp[i] = sacc;
                 }
-                chol_tmp[c] = ycc;
+                __syncwarp();
+                const double dj = chol_tmp[j];
+                if (!(dj > thr)) {
+                    ok = false;
+                } else {
+                    const double root = sqrt(dj);
+                    for (int i = j + lane; i < k; i += 32)
+                        V[i * kJacLd + j] = (i == j) ? root : chol_tmp[i] / root;
+                }
+                __syncwarp();
             }
-            __syncwarp();
-        }
-        if (lane == 0) chol_ok = ok ? 1 : 0;
-    }
-    __syncthreads();
-    if (chol_ok) {
-        // (L^-1)[i][c] = V[c][i] for i > c, chol_tmp[c] for i == c;  P = L^-T L^-1
-        for (int idx = tid; idx < k * k; idx += blockDim.x) {
-            const int a = idx / k, b = idx % k;
-            const int lo = a > b ? a : b;
-            double sacc = 0.0;
-            for (int i = lo; i < k; ++i) {
-                const double la = (i == a) ? chol_tmp[a] : V[a * kJacLd + i];
-                const double lb = (i == b) ? chol_tmp[b] : V[b * kJacLd + i];
-                sacc = fma(la, lb, sacc);
+            if (ok) {
+                // columns of L^-1 by forward substitution (one column per lane), stored in A's
+                // upper part is not safe (A may still be needed) -> reuse chol-free rows of V:
+                // L^-1 overwrites the strictly-upper triangle + a separate diagonal pass
+                for (int c = lane; c < k; c += 32) {
+                    // y = L^-1 e_c, kept in the upper triangle V[c][i] (i >= c)
+                    double ycc = 1.0 / V[c * kJacLd + c];
+                    for (int i = c + 1; i < k; ++i) {
+                        double sacc = V[i * kJacLd + c] * ycc;
+                        for (int q = c + 1; q < i; ++q) sacc = fma(V[i * kJacLd + q], V[c * kJacLd + q], sacc);
+                        V[c * kJacLd + i] = -sacc / V[i * kJacLd + i];
+                    }
+                    chol_tmp[c] = ycc;
+                }
+                __syncwarp();
             }
-            P[idx] = sacc * inv_n;
+            if (lane == 0) chol_ok = ok ? 1 : 0;
         }
-        return;                                   // CTA-uniform
+        __syncthreads();
+        if (chol_ok) {
+            // (L^-1)[i][c] = V[c][i] for i > c, chol_tmp[c] for i == c;  P = L^-T L^-1
+            for (int idx = tid; idx < k * k; idx += blockDim.x) {
+                const int a = idx / k, b = idx % k;
+                const int lo = a > b ? a : b;
+                double sacc = 0.0;
+                for (int i = lo; i < k; ++i) {
+                    const double la = (i == a) ? chol_tmp[a] : V[a * kJacLd + i];
+                    const double lb = (i == b) ? chol_tmp[b] : V[b * kJacLd + i];
+                    sacc = fma(la, lb, sacc);
+                }
+                P[idx] = sacc * inv_n;
+            }
+            return;                                   // CTA-uniform
+        }
     }
     for (int idx = tid; idx < k * k; idx += blockDim.x) {
         const int i = idx / k, j = idx % k;

@@ -51,6 +51,8 @@ for n_it in (6, 26):
     print('tail marks: enter %.2f, partials summed %.2f, cost checks done %.2f, before solve %.2f, end %.2f us' % tuple(tm))
     qp = (ph[2, :nw].astype(np.int64) - ph[1, :nw].astype(np.int64)) / 1e3
     ni, nf = ph[6, :nw].astype(np.int64), ph[7, :nw].astype(np.int64)
+    print('iterations per sample: mean %.1f, max %d; function evaluations: mean %.1f, max %d'
+          % ((ni + 1).mean(), (ni + 1).max(), nf.mean(), nf.max()))
     order = np.argsort(qp)[::-1][:8]
     print('slowest samples: qp us', np.round(qp[order], 2), 'n_iter', ni[order], 'n_feval', nf[order])
     A = np.stack([ni + 1, nf, np.ones(nw)], axis=1).astype(float)

@@ -37,6 +37,7 @@ enum { RS_A0 = 0, RS_ROWMAX = 1, RS_DELTA = 2, RS_DD = 3, RS_A1 = 4, RS_BETA = 5
 
 constexpr int kAaRowMaxT = 26000;      // aa_steps.cu: rows are staged in shared memory
 constexpr int kAaStagedMaxT = 6000;    // head kernel: four row buffers of T doubles (<= 188 KB)
+constexpr int kAaStagedXMaxT = 13500;  // ... or two (the projected row only)
 
 // gradient entry (j, t):  s_g * (sum_i a_j a_i ZtZ[j][i] CK[i][t] - a_j KZt[j][t]), k <= 16;
 // coef[i] = a_j a_i ZtZ[j][i], 0 for i >= k (adding 0 * 0 leaves the sum -- formed in the order
@@ -91,10 +92,11 @@ __device__ unsigned long long cdr_head_ns[16 * 16];
 #endif
 
 // ---------------------------------------------------------------------- kernel 1
-// grad_ready: G already holds df(x) (aa_kzt_gradient_kernel / aa_initial_gradient_kernel wrote it with
+// grad_ready: G already holds df(x) (aa_kzt_gradient_kernel / aa_gradient_columns_kernel wrote it with
 // the (K Z)' it belongs to; the gradient uses the maintained C K, not the re-projected x).
-// staged: the row's x, g and (K Z)' are kept in shared memory next to `work` (4 T doubles);
-// otherwise -- long rows of a sample-sharded fit -- they are re-read from global memory.
+// staged: 2 = the row's x, g and (K Z)' are kept in shared memory next to `work` (4 T
+// doubles), 1 = x only (2 T doubles), 0 = long rows of a large sample-sharded fit: they are
+// re-read from global memory.
 __global__ void __launch_bounds__(1024)
 aa_head_kernel(cdr_aa_buffers b, cdr_spg_params p, int grad_ready, int staged)
 {
@@ -112,12 +114,12 @@ aa_head_kernel(cdr_aa_buffers b, cdr_spg_params p, int grad_ready, int staged)
     const double* kzrow = b.KZt + (long)j * b.ldt;
     // generic pointers: shared-memory copies when staged, the global rows otherwise
     double* xs = staged ? work + T : crow;
-    double* gs = staged ? work + 2 * (long)T : grow;
-    const double* kz = staged ? work + 3 * (long)T : kzrow;
+    double* gs = (staged == 2) ? work + 2 * (long)T : grow;
+    const double* kz = (staged == 2) ? work + 3 * (long)T : kzrow;
 
     // the loads below do not depend on `done` (issued together with its read); the three rows
     // of a staged launch go out together, eight elements per thread before the first store
-    if (staged) {
+    if (staged == 2) {
         double* xw = work;                              // known shared-memory pointers: the
         double* gw = work + 2 * (long)T;                // loads can be hoisted over the stores
         double* kw = work + 3 * (long)T;
@@ -177,11 +179,11 @@ aa_head_kernel(cdr_aa_buffers b, cdr_spg_params p, int grad_ready, int staged)
             const double g = aa_grad_entry16(b, coef, j, t);
             const double g2 = (t2 < T) ? aa_grad_entry16(b, coef, j, t2) : 0.0;
             grow[t] = g;
-            if (staged) gs[t] = g;
+            if (staged == 2) gs[t] = g;
             work[t] = xs[t] - g;
             if (t2 < T) {
                 grow[t2] = g2;
-                if (staged) gs[t2] = g2;
+                if (staged == 2) gs[t2] = g2;
                 work[t2] = xs[t2] - g2;
             }
         }
@@ -678,8 +680,9 @@ aa_kzt_gradient_kernel(const double* __restrict__ part, int nstrips, cdr_aa_buff
     }
 }
 
-// The gradient alone, from (K Z)' in memory (after cdr_aa_prepare_enqueue): one sample per thread.
-__global__ void __launch_bounds__(256) aa_initial_gradient_kernel(cdr_aa_buffers b)
+// The gradient alone, from (K Z)' in memory (after cdr_aa_prepare_enqueue; before the head kernel
+// of a sample-sharded iteration): one sample per thread.
+__global__ void __launch_bounds__(256) aa_gradient_columns_kernel(cdr_aa_buffers b)
 {
     if (is_done(b.state)) return;
     __shared__ double coef[kFusedMaxK * kFusedMaxK];
@@ -906,7 +909,7 @@ extern "C" int cdr_aa_prepare_enqueue(const cdr_aa_problem* p, cdr_stream_t stre
     CDR_TRY(cdr_small_gram(ds, 1, w.gram, w.gram_bytes, b.state, s));
     // df(x) of the first dictionary step (the eight-kernel iteration expects it in G)
     if (k <= kFusedMaxK) {
-        aa_initial_gradient_kernel<<<(b.T + 255) / 256, 256, 0, s>>>(b);
+        aa_gradient_columns_kernel<<<(b.T + 255) / 256, 256, 0, s>>>(b);
         CDR_RETURN_IF_LAUNCH_FAILED();
     }
     return cdr_loop_begin(b.state, s);
@@ -962,10 +965,18 @@ extern "C" int cdr_aa_iterate_enqueue(const cdr_aa_problem* p, cdr_stream_t stre
         // the rows of the (replicated) dictionary span all samples; short rows keep x, g and
         // (K Z)' in shared memory as well.  On one GPU the gradient was left in G by
         // cdr_aa_prepare_enqueue / the previous iteration's last kernel.
-        const int staged = (b.T <= kAaStagedMaxT) ? 1 : 0;
-        const size_t smem = (64 + CDR_MAX_COMPONENTS + (size_t)(staged ? 4 : 1) * b.T) * sizeof(double);
+        const int staged = (b.T <= kAaStagedMaxT) ? 2 : (b.T <= kAaStagedXMaxT) ? 1 : 0;
+        const size_t smem =
+            (64 + CDR_MAX_COMPONENTS + (size_t)(staged == 2 ? 4 : staged == 1 ? 2 : 1) * b.T) * sizeof(double);
         CDR_TRY(ensure_dyn_smem<aa_head_kernel>(smem));
-        aa_head_kernel<<<k, aa_row_threads(b.T), smem, s>>>(b, dp, sharded ? 0 : 1, staged);
+        if (sharded) {
+            // the replicated (K Z)' was completed by the exchange that ended the previous
+            // iteration: the gradient of all T_total columns as one wide launch (inside the
+            // head kernel it is k CTAs x (k + 1) T_total loads: 35 us at 8 x 1620 samples)
+            aa_gradient_columns_kernel<<<(b.T + 255) / 256, 256, 0, s>>>(b);
+            CDR_RETURN_IF_LAUNCH_FAILED();
+        }
+        aa_head_kernel<<<k, aa_row_threads(b.T), smem, s>>>(b, dp, 1, staged);
         CDR_RETURN_IF_LAUNCH_FAILED();
     }
     // 2. D X (summed over ranks in the kernel's epilogue when sharded)

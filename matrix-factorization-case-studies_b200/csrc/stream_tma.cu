@@ -60,7 +60,7 @@ reduce_samples_tma_kernel(const double* __restrict__ Lp, long sLi, long sLt,
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
     double* Es = reinterpret_cast<double*>(smem_raw + 128);
     double* epi = Es + (FUSE_E ? KP * KP : 0);
-    double* tiles = epi + (FUSE_E ? kConsumerWarps * KP * 20 : 0);
+    double* tiles = epi + ((FUSE_E || kExchange) ? kConsumerWarps * KP * 20 : 0);
     const int RS = TC + 4;                       // row stride (doubles): == 4 mod 16, conflict free
     const long stage_doubles = (long)kSampTR * RS;
 
@@ -214,10 +214,8 @@ reduce_samples_tma_kernel(const double* __restrict__ Lp, long sLi, long sLt,
                     if (i < k) {
                         const long el = (long)i * ldo + fbase + 4 * lr;
                         if constexpr (kExchange) {
-                            emit(el, acc[u][mt][0][0]);
-                            emit(el + 1, acc[u][mt][1][0]);
-                            emit(el + 2, acc[u][mt][0][1]);
-                            emit(el + 3, acc[u][mt][1][1]);
+                            // (handled below: the tile goes through shared memory so that the
+                            // tagged words leave in 256-byte runs)
                         } else {
                             double* p = out + el;
                             *reinterpret_cast<double2*>(p) =
@@ -226,6 +224,24 @@ reduce_samples_tma_kernel(const double* __restrict__ Lp, long sLi, long sLt,
                                 make_double2(acc[u][mt][0][1], acc[u][mt][1][1]);
                         }
                     }
+                }
+                if constexpr (kExchange) {
+                    // peer stores of 16 bytes with a 64-byte stride use a fraction of the link
+                    // (r02n: +70 us per pass at 8 GPUs against +48 us for the variant below,
+                    // whose lanes write consecutive words): same staging here
+                    double* eb = epi + warp * (KP * 20);
+#pragma unroll
+                    for (int mt = 0; mt < KT; ++mt) {
+                        double* p = eb + (mt * 8 + lc) * 20 + 4 * lr;
+                        p[0] = acc[u][mt][0][0];
+                        p[1] = acc[u][mt][1][0];
+                        p[2] = acc[u][mt][0][1];
+                        p[3] = acc[u][mt][1][1];
+                    }
+                    __syncwarp();
+                    const int f = lane & 15, jh = lane >> 4;
+                    for (int j = jh; j < k; j += 2) emit((long)j * ldo + fbase + f, eb[j * 20 + f]);
+                    __syncwarp();
                 }
             } else {
                 double* eb = epi + warp * (KP * 20);
@@ -265,6 +281,10 @@ reduce_samples_tma_kernel(const double* __restrict__ Lp, long sLi, long sLt,
                 for (int idx = threadIdx.x; idx < k * w; idx += kConsumerWarps * 32) {
                     const int i = idx / w, c = idx - i * w;
                     const long el = (long)i * ldo + c0 + c;
+                    // (requesting the word pairs of all ranks at once and polling only the
+                    // late ones was measured at 8 GPUs: 162 us per pass against 148 us for
+                    // this loop, profiles/r02/r02z_launch_timing_n8_poll_ab.txt -- the wait is
+                    // for the data to arrive, not for the polls)
                     double sum = 0.0;
                     for (int r = 0; r < g.world; ++r) {
                         const unsigned long long* src = reinterpret_cast<const unsigned long long*>(
@@ -667,9 +687,10 @@ static int ring_stages(size_t fixed_bytes, size_t stage_bytes)
     return stages > kMaxStages ? kMaxStages : stages;
 }
 
-static size_t samples_fixed_smem(int kp, bool fuse_e)
+static size_t samples_fixed_smem(int kp, bool fuse_e, bool exchange = false)
 {
-    return 128 + (fuse_e ? ((size_t)kp * kp + (size_t)kConsumerWarps * kp * 20) * 8 : 0);
+    return 128 + (fuse_e ? (size_t)kp * kp * 8 : 0) +
+           ((fuse_e || exchange) ? (size_t)kConsumerWarps * kp * 20 * 8 : 0);
 }
 
 // Strip plan of the reduce over samples; false when the direct-load (split-T) kernels should
@@ -739,7 +760,7 @@ static int launch_samples_exchange(const cdr_peer_group& g, size_t out_offset, c
                                    const cdr_flags* flags, cudaStream_t stream)
 {
     constexpr int KP = 8 * KT;
-    const size_t fixed = samples_fixed_smem(KP, FUSE_E);
+    const size_t fixed = samples_fixed_smem(KP, FUSE_E, true);
     const size_t stage = (size_t)kSampTR * (TC + 4) * 8;
     const int stages = ring_stages(fixed, stage);
     if (stages < 2) return CDR_ERR_NOT_APPLICABLE;

@@ -15,7 +15,7 @@ from convex_dim_red.datasets import synthetic_field           # noqa: E402
 from convex_dim_red.stochastic_matrices import right_stochastic_matrix   # noqa: E402
 import bench_harness as bh                                    # noqa: E402
 
-T, d, k = 1620, 44000, 8
+T, d, k = int(os.environ.get('PROFILE_T', '1620')), 44000, 8
 X = synthetic_field(T, d, seed=0)
 Z0 = right_stochastic_matrix((T, k), np.random.RandomState(1000))
 C0 = right_stochastic_matrix((k, T), np.random.RandomState(7))

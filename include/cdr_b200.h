@@ -499,11 +499,15 @@ typedef struct cdr_aa_problem {
 
 size_t cdr_aa_workspace_bytes(int T, int d, int k);
 /* archetypal_analysis.py:541-556: C X X', X X' Z, Z'Z, C X X' C', the initial cost; then the
- * projection of the start that spg() applies first (spg.py:146-148) and old_cost. */
+ * projection of the start that spg() applies first (spg.py:146-148), old_cost, and the
+ * gradient of the first dictionary step in buf.G. */
 int cdr_aa_prepare_enqueue(const cdr_aa_problem* problem, cdr_stream_t stream);
 /* archetypal_analysis.py:586-663: dictionary SPG step(s), weights update, both cost checks,
  * stopping rule.  With one inner iteration and k <= 16 at streaming shapes
- * (cdr_aa_fused_applicable) this is eight kernels, see csrc/iterate_aa.cu. */
+ * (cdr_aa_fused_applicable) this is eight kernels, see csrc/iterate_aa.cu.  The buffers carry
+ * the state from call to call (C, CK, KZt, the k x k statistics and, on the eight-kernel path
+ * of a single GPU, the gradient of the next dictionary step in buf.G): call it on what
+ * cdr_aa_prepare_enqueue or the previous call left. */
 int cdr_aa_iterate_enqueue(const cdr_aa_problem* problem, cdr_stream_t stream);
 int cdr_aa_fused_applicable(int T, int d, int k, int dictionary_max_iterations);
 

@@ -9,8 +9,9 @@
 // at streaming shapes that is eight kernels here:
 //
 //   1. aa_head_kernel (one CTA per dictionary row, one grid barrier): x = P(C) (spg.py:148),
-//      the linear trace term, df(x), the first step length 1 / max|P(x - g) - x| (spg.py:178-189),
-//      d = P(x - alpha g) - x and the row partials of <d,g>, <d,d> (spg.py:191-206)
+//      the linear trace term, the first step length 1 / max|P(x - g) - x| (spg.py:178-189),
+//      d = P(x - alpha g) - x and the row partials of <d,g>, <d,d> (spg.py:191-206); the
+//      gradient g = df(x) was left in G by kernel 8 of the previous iteration
 //   2. reduce over samples   D X                        (stream_tma.cu)
 //   3. reduce over features  (D X) X' as per-strip partials
 //   4. aa_finalize_ls_kernel: D K = sum of the strip partials, and per 32-sample block the
@@ -22,7 +23,9 @@
 //      (:344-366), and the statistics z z', tr(C K Z); the last CTA sums them, applies the cost
 //      check after the weights update and the stopping rule (:645-663) and starts the next
 //      iteration
-//   6.-8. (K Z)' = X (X' Z): reduce over samples, reduce over features + finalize (:641-642)
+//   6.-8. (K Z)' = X (X' Z): reduce over samples, reduce over features, and
+//      aa_kzt_gradient_kernel: sum of the strip partials (:641-642) plus the gradient of the
+//      next dictionary step for the same columns (:293-299)
 //
 // Other configurations (more inner SPG iterations, k > 16, small or Gram-space problems) run
 // the general kernel sequence of aa_steps.cu.  All reductions have a fixed order.

@@ -16,24 +16,23 @@ constexpr int kFusedWarps = 8;                 // warps per CTA of the fused wei
 constexpr int kFusedThreads = kFusedWarps * 32;
 constexpr int kFusedMaxK = 16;
 
-// fixed-order sum of n values spaced `stride` doubles apart, read around L1
-__device__ __forceinline__ double strided_sum_cg(const double* base, long stride, int n)
+// fixed-order sum of n values spaced `stride` doubles apart, read around L1, 32 loads in
+// flight (the tail of the last batch reads nothing and adds zeros)
+__device__ __forceinline__ double strided_sum_cg32(const double* base, long stride, int n)
 {
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int i = 0;
-    for (; i + 16 <= n; i += 16) {
-        double v[16];
+    for (int i = 0; i < n; i += 32) {
+        double v[32];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = __ldcg(base + (long)(i + q) * stride);
+        for (int q = 0; q < 32; ++q) v[q] = (i + q < n) ? __ldcg(base + (long)(i + q) * stride) : 0.0;
 #pragma unroll
-        for (int q = 0; q < 16; q += 4) {
+        for (int q = 0; q < 32; q += 4) {
             a0 += v[q];
             a1 += v[q + 1];
             a2 += v[q + 2];
             a3 += v[q + 3];
         }
     }
-    for (; i < n; ++i) a0 += __ldcg(base + (long)i * stride);
     return (a0 + a1) + (a2 + a3);
 }
 
@@ -121,26 +120,6 @@ __device__ __forceinline__ bool fused_sample_statistics(const double (&x)[KPL],
     const bool last = is_last != 0;
     if (last) __threadfence();
     return last;
-}
-
-// fixed-order sum of n values spaced `stride` doubles apart, 32 loads in flight (the tail of
-// the last batch reads nothing and adds zeros)
-__device__ __forceinline__ double strided_sum_cg32(const double* base, long stride, int n)
-{
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    for (int i = 0; i < n; i += 32) {
-        double v[32];
-#pragma unroll
-        for (int q = 0; q < 32; ++q) v[q] = (i + q < n) ? __ldcg(base + (long)(i + q) * stride) : 0.0;
-#pragma unroll
-        for (int q = 0; q < 32; q += 4) {
-            a0 += v[q];
-            a1 += v[q + 1];
-            a2 += v[q + 2];
-            a3 += v[q + 3];
-        }
-    }
-    return (a0 + a1) + (a2 + a3);
 }
 
 // Last CTA: fin[0..NST) = sum over the CTAs of the grid of cta_part, fixed order.

@@ -110,7 +110,7 @@ gpnh_weights_fused_kernel(GpnhFusedArgs a)
         const long stride = (long)helpers * T * KP;
 #pragma unroll
         for (int r = 0; r < KPL; ++r) {
-            double v = strided_sum_cg(base + r, stride, n_mine);
+            double v = strided_sum_cg32(base + r, stride, n_mine);
             // combine the phases in fixed order (every lane group ends up with the total)
             double tot = __shfl_sync(CDR_FULL_MASK, v, (q % spw) * 8 + g);
             for (int ph = 1; ph < helpers; ++ph)

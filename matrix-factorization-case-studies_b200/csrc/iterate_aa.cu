@@ -309,6 +309,19 @@ __global__ void __launch_bounds__(kFinThreads) aa_finalize_ls_kernel(AaFinalizeA
     const int t0 = blockIdx.x * kFinTB;
     const bool sharded = a.g.world > 1;
 
+    // the block's columns of C, D and C K: requested first, so that the loads overlap the
+    // partial sums below (one L2 round trip less on the kernel's critical path)
+    constexpr int kTileLoads = (3 * KP * kFinTB + kFinThreads - 1) / kFinThreads;    // 1 | 2
+    double tile_v[kTileLoads];
+#pragma unroll
+    for (int u = 0; u < kTileLoads; ++u) {
+        const int idx = threadIdx.x + u * kFinThreads;
+        const int which = idx / (KP * kFinTB), rem = idx % (KP * kFinTB);
+        const int i = rem / kFinTB, t = t0 + rem % kFinTB;
+        const double* src = (which == 0) ? b.C : (which == 1) ? b.D : b.CK;
+        tile_v[u] = (idx < 3 * KP * kFinTB && i < k && t < T) ? src[(long)i * ldt + a.row0 + t] : 0.0;
+    }
+
     // ---- D K for this block of samples: sum of the per-strip partials, fixed order
     {
         const int item = threadIdx.x % ITEMS, grp = threadIdx.x / ITEMS;
@@ -318,11 +331,19 @@ __global__ void __launch_bounds__(kFinThreads) aa_finalize_ls_kernel(AaFinalizeA
         if (t < T) {
             const double2* src = reinterpret_cast<const double2*>(part) + ((long)t * PAIRS + pr);
             const long stride = (long)T * PAIRS;
-#pragma unroll 6
-            for (int s = grp; s < nstrips; s += GROUPS) {
-                const double2 v = __ldcg(src + (long)s * stride);
-                s0 += v.x;
-                s1 += v.y;
+            // all of a thread's strips in flight at once (<= 24 of them: nstrips <= 148 + ...)
+            for (int s = grp; s < nstrips; s += 24 * GROUPS) {
+                double2 v[24];
+#pragma unroll
+                for (int q = 0; q < 24; ++q) {
+                    const int sq = s + q * GROUPS;
+                    v[q] = (sq < nstrips) ? __ldcg(src + (long)sq * stride) : make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int q = 0; q < 24; ++q) {
+                    s0 += v[q].x;
+                    s1 += v[q].y;
+                }
             }
         }
         red[grp][item] = make_double2(s0, s1);
@@ -351,12 +372,13 @@ __global__ void __launch_bounds__(kFinThreads) aa_finalize_ls_kernel(AaFinalizeA
             tiles[3][j0 + 1][tl] = (ok && j0 + 1 < k) ? a1 : 0.0;
         }
     }
-    for (int idx = threadIdx.x; idx < 3 * KP * kFinTB; idx += blockDim.x) {
-        const int which = idx / (KP * kFinTB), rem = idx % (KP * kFinTB);
-        const int i = rem / kFinTB, tl = rem % kFinTB;
-        const int t = t0 + tl;
-        const double* src = (which == 0) ? b.C : (which == 1) ? b.D : b.CK;
-        tiles[which][i][tl] = (i < k && t < T) ? src[(long)i * ldt + a.row0 + t] : 0.0;
+#pragma unroll
+    for (int u = 0; u < kTileLoads; ++u) {
+        const int idx = threadIdx.x + u * kFinThreads;
+        if (idx < 3 * KP * kFinTB) {
+            const int which = idx / (KP * kFinTB), rem = idx % (KP * kFinTB);
+            tiles[which][rem / kFinTB][rem % kFinTB] = tile_v[u];
+        }
     }
     __syncthreads();
 
@@ -389,8 +411,14 @@ __global__ void __launch_bounds__(kFinThreads) aa_finalize_ls_kernel(AaFinalizeA
             const int n_mine = (nblk - ph + PH - 1) / PH;
             double s = 0.0;
             const double* src = cta_part + (long)ph * NOUT + e;
-#pragma unroll 4
-            for (int q = 0; q < n_mine; ++q) s += __ldcg(src + (long)q * PH * NOUT);
+            for (int q0 = 0; q0 < n_mine; q0 += 16) {           // 16 loads in flight, same order
+                double v[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q)
+                    v[q] = (q0 + q < n_mine) ? __ldcg(src + (long)(q0 + q) * PH * NOUT) : 0.0;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) s += v[q];
+            }
             phs[ph * NOUT + e] = s;
         }
         __syncthreads();
@@ -646,17 +674,17 @@ aa_kzt_gradient_kernel(const double* __restrict__ part, int nstrips, cdr_aa_buff
     if (item < nitems) {
         const double2* src = reinterpret_cast<const double2*>(part) + item;
         const int hi = min(nstrips, (grp + 1) * per);
-        int sidx = grp * per;
-        for (; sidx + 2 <= hi; sidx += 2) {
-            const double2 v0 = src[(long)sidx * stride];
-            const double2 v1 = src[(long)(sidx + 1) * stride];
-            s0 += v0.x; s1 += v0.y;
-            s0 += v1.x; s1 += v1.y;
-        }
-        for (; sidx < hi; ++sidx) {
-            const double2 v = src[(long)sidx * stride];
-            s0 += v.x;
-            s1 += v.y;
+        // 24 strips in flight (all of a group's strips at the usual widths), summed in order
+        for (int s_lo = grp * per; s_lo < hi; s_lo += 24) {
+            double2 v[24];
+#pragma unroll
+            for (int q = 0; q < 24; ++q)
+                v[q] = (s_lo + q < hi) ? src[(long)(s_lo + q) * stride] : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int q = 0; q < 24; ++q) {
+                s0 += v[q].x;
+                s1 += v[q].y;
+            }
         }
     }
     red[grp][lane] = make_double2(s0, s1);
@@ -725,17 +753,17 @@ features_finalize_push_kernel(const double* __restrict__ part, int Tl, int nstri
     if (item < nitems) {
         const double2* src = reinterpret_cast<const double2*>(part) + item;
         const int hi = min(nstrips, (grp + 1) * per);
-        int sidx = grp * per;
-        for (; sidx + 2 <= hi; sidx += 2) {
-            const double2 v0 = src[(long)sidx * stride];
-            const double2 v1 = src[(long)(sidx + 1) * stride];
-            s0 += v0.x; s1 += v0.y;
-            s0 += v1.x; s1 += v1.y;
-        }
-        for (; sidx < hi; ++sidx) {
-            const double2 v = src[(long)sidx * stride];
-            s0 += v.x;
-            s1 += v.y;
+        // 24 strips in flight (all of a group's strips at the usual widths), summed in order
+        for (int s_lo = grp * per; s_lo < hi; s_lo += 24) {
+            double2 v[24];
+#pragma unroll
+            for (int q = 0; q < 24; ++q)
+                v[q] = (s_lo + q < hi) ? src[(long)(s_lo + q) * stride] : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int q = 0; q < 24; ++q) {
+                s0 += v[q].x;
+                s1 += v[q].y;
+            }
         }
     }
     red[grp][lane] = make_double2(s0, s1);

@@ -583,17 +583,17 @@ reduce_features_strip_finalize_kernel(const double* __restrict__ part, int T, in
     if (item < nitems) {
         const double2* src = reinterpret_cast<const double2*>(part) + item;
         const int hi = min(nstrips, (g + 1) * per);
-        int sidx = g * per;
-        for (; sidx + 2 <= hi; sidx += 2) {
-            const double2 v0 = src[(long)sidx * stride];
-            const double2 v1 = src[(long)(sidx + 1) * stride];
-            s0 += v0.x; s1 += v0.y;
-            s0 += v1.x; s1 += v1.y;
-        }
-        for (; sidx < hi; ++sidx) {
-            const double2 v = src[(long)sidx * stride];
-            s0 += v.x;
-            s1 += v.y;
+        // 24 strips in flight (all of a group's strips at the usual widths), summed in order
+        for (int s_lo = g * per; s_lo < hi; s_lo += 24) {
+            double2 v[24];
+#pragma unroll
+            for (int q = 0; q < 24; ++q)
+                v[q] = (s_lo + q < hi) ? src[(long)(s_lo + q) * stride] : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int q = 0; q < 24; ++q) {
+                s0 += v[q].x;
+                s1 += v[q].y;
+            }
         }
     }
     red[g][lane] = make_double2(s0, s1);

@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libcdr_b200.so')
+# CDR_LIBRARY: another build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get('CDR_LIBRARY') or os.path.join(_HERE, 'libcdr_b200.so')
 
 LD_ALIGN = 32
 MAX_COMPONENTS = 64

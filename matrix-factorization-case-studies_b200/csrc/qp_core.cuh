@@ -22,6 +22,15 @@ __device__ __forceinline__ double group8_max(double v)
     return v;
 }
 
+// line-search trials a lane group evaluates per round in the halving regime.  Eight (one round
+// of four replicas would cover the 32 halvings from 1 down past lambda_min = 1e-10) was
+// measured against four on the same box: AA 0.4341 vs 0.4347 ms, GPNH 0.2445 vs 0.2369 ms per
+// iteration (128 registers and a spill in the fused kernel) -> four.
+#ifndef CDR_QP_TRIALS
+#define CDR_QP_TRIALS 4
+#endif
+constexpr int kQpTrials = CDR_QP_TRIALS;
+
 template <int KPL>
 struct QpMatVec {
     // y = A' x for the lane's KPL components.  As: transposed A' in shared
@@ -174,8 +183,8 @@ __device__ __forceinline__ void qp_solve(const double* As, const double (&arow)[
         // Backtracking.  Once sigma_two * lam < sigma_one the safeguarded interpolation of
         // spg.py:19-33 can only return lam / 2 (its acceptance interval is empty), so the
         // following trial steps l0, l0/2, l0/4, ... are known in advance.  They are evaluated
-        // 4 * replicas at a time -- four per lane group (four independent 8-lane reductions in
-        // flight), and when several lane groups of the warp hold the same sample (small
+        // kQpTrials * replicas at a time -- four per lane group (four independent 8-lane
+        // reductions in flight), and when several lane groups of the warp hold the same sample (small
         // batches: one sample per warp, see the callers) each replica takes its own four --
         // and then examined in order, exactly as the reference would.  This is where the
         // samples with rounding-level Armijo failures spend their time (~33 halvings per
@@ -186,17 +195,18 @@ __device__ __forceinline__ void qp_solve(const double* As, const double (&arow)[
             const double l0 = searching ? spg_step_length(lam, delta, f_old, f_new, p.sigma_one,
                                                           p.sigma_two)
                                         : lam;
-            const int first = halving ? 4 * replica : 0;         // this group's first trial
-            double lt[4];
-            lt[0] = l0 * (1.0 / (double)(1 << first));           // exact power-of-two scaling
-            lt[1] = 0.5 * lt[0];
-            lt[2] = 0.5 * lt[1];
-            lt[3] = 0.5 * lt[2];
-            double st[4] = {0.0, 0.0, 0.0, 0.0};
+            const int first = halving ? kQpTrials * replica : 0;   // this group's first trial
+            double lt[kQpTrials];
+            lt[0] = l0 * (1.0 / (double)(1ull << first));          // exact power-of-two scaling
+#pragma unroll
+            for (int j = 1; j < kQpTrials; ++j) lt[j] = 0.5 * lt[j - 1];
+            double st[kQpTrials];
+#pragma unroll
+            for (int j = 0; j < kQpTrials; ++j) st[j] = 0.0;
 #pragma unroll
             for (int r = 0; r < KPL; ++r) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < kQpTrials; ++j) {
                     const double xt = xo[r] + lt[j] * dk[r];
                     st[j] += xt * (0.5 * (Ax[r] + lt[j] * Ad[r]) + b[r]);
                 }
@@ -204,14 +214,14 @@ __device__ __forceinline__ void qp_solve(const double* As, const double (&arow)[
 #pragma unroll
             for (int o = 4; o > 0; o >>= 1) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) st[j] += __shfl_xor_sync(CDR_FULL_MASK, st[j], o, 8);
+                for (int j = 0; j < kQpTrials; ++j) st[j] += __shfl_xor_sync(CDR_FULL_MASK, st[j], o, 8);
             }
             // first trial of this group at which the search ends (step below lambda_min, or
             // the Armijo condition holds): 99 = none
-            const int nvalid = halving ? 4 : 1;
+            const int nvalid = halving ? kQpTrials : 1;
             int stop = 99;
 #pragma unroll
-            for (int j = 3; j >= 0; --j) {
+            for (int j = kQpTrials - 1; j >= 0; --j) {
                 const bool ends = (fabs(lt[j]) < p.lambda_min) ||
                                   !(st[j] > f_max + p.gamma * lt[j] * delta);
                 if (j < nvalid && ends) stop = first + j;
@@ -223,14 +233,16 @@ __device__ __forceinline__ void qp_solve(const double* As, const double (&arow)[
             for (int rho = 0; rho < 4; ++rho)
                 m = min(m, __shfl_sync(CDR_FULL_MASK, stop,
                                        (sample_group + spw * (rho & (replicas - 1))) * 8 + g));
-            const int round_trials = halving ? 4 * replicas : 1;
+            const int round_trials = halving ? kQpTrials * replicas : 1;
             const int last = (m == 99) ? round_trials - 1 : m;   // the trial the search is at now
-            const int jsel = last & 3;
-            const double fsel = (jsel == 0) ? st[0] : (jsel == 1) ? st[1] : (jsel == 2) ? st[2] : st[3];
-            const double f_at = __shfl_sync(CDR_FULL_MASK, fsel,
-                                            (sample_group + spw * (halving ? last >> 2 : 0)) * 8 + g);
+            const int jsel = last % kQpTrials;
+            double fsel = st[0];
+#pragma unroll
+            for (int j = 1; j < kQpTrials; ++j) fsel = (jsel == j) ? st[j] : fsel;
+            const double f_at = __shfl_sync(
+                CDR_FULL_MASK, fsel, (sample_group + spw * (halving ? last / kQpTrials : 0)) * 8 + g);
             if (searching) {
-                lam = l0 * (1.0 / (double)(1 << last));
+                lam = l0 * (1.0 / (double)(1ull << last));
                 f_new = f_at;
                 fe += last + 1;
                 searching = (m == 99);

@@ -174,6 +174,32 @@ def test_aa_full_size_vs_oracle(hadisst):
     _close(got[1], ref[1], rtol=0, atol=2e-5)
 
 
+@pytest.mark.parametrize('n_rows', [7000, 14000])
+def test_aa_long_dictionary_rows_vs_oracle(n_rows):
+    """The eight-kernel iteration with dictionary rows too long for the head kernel's
+    all-in-shared-memory layout: 6000 < T <= 13500 keeps only the projected row resident,
+    longer rows are re-read from global memory (csrc/iterate_aa.cu).  On one GPU these layouts
+    are reached only with many samples; sample-sharded fits reach them through T_total."""
+    d, k = 9600, 5
+    assert be.library().cdr_aa_fused_applicable(n_rows, d, k, 1) == 1
+    X = synthetic_field(n_rows, d, seed=31)
+    rs = np.random.RandomState(32)
+    C0 = right_stochastic_matrix((k, n_rows), random_state=rs)
+    Z0 = right_stochastic_matrix((n_rows, k), random_state=rs)
+    trace = float(np.sum(X * X))
+    kw = dict(tolerance=1e-12, max_iterations=3, dictionary_solver_kwargs=dict(max_iterations=1))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ref = orc.iterate_aa(X, Z0.copy(), C0.copy(), np.ones(k), trace_XXt=trace, **kw)
+        got = aa._iterate_aa(X, Z0.copy(), C0.copy(), np.ones(k), **kw)
+    assert got[4] == ref[4] == 2
+    _close(got[3], ref[3], rtol=1e-8)
+    _close(got[6], ref[6], rtol=1e-5, atol=1e-9)
+    _close(got[0], ref[0], rtol=0, atol=2e-5)
+    _close(got[1], ref[1], rtol=0, atol=2e-5)
+
+
 def test_aa_full_size_inner_spg_iterations_vs_oracle(hadisst):
     """Two inner SPG iterations per dictionary update exercise the Barzilai-Borwein step and
     the residual test of spg.py:231-281 at full size."""

@@ -49,23 +49,25 @@ kmeans_begin_kernel(const double* __restrict__ C, long ldc, int d, int k, double
     }
 }
 
-// 3. assignment from the per-strip partials part[strip][t][8] (k <= 8): an aligned group of 8
-// lanes owns a sample, lane c component c; the four groups of a warp split the strips of one
-// sample and combine in fixed order
+// 2. assignment from the per-strip partials part[strip][t][KP] (KP = 8 for k <= 8, 16 for
+// k <= 16): an aligned group of KP lanes owns a sample, lane c component c; the 32 / KP groups
+// of a warp split the strips of one sample and combine in fixed order
+template <int KP>
 __global__ void __launch_bounds__(256)
 kmeans_assign_kernel(const double* __restrict__ part, int nstrips, const double* __restrict__ cnorm,
                      int T, int k, int32_t* labels, double* onehot, long ldo, int* counts,
                      cdr_kmeans_state* st)
 {
     if (km_done(st)) return;
-    const int lane = threadIdx.x & 31, g = lane & 7, q = lane >> 3;
+    constexpr int PHASES = 32 / KP;
+    const int lane = threadIdx.x & 31, g = lane % KP, q = lane / KP;
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // one sample per warp
     if (t >= T) return;
     double a0 = 0.0, a1 = 0.0;
     {
-        const double* base = part + ((long)q * T + t) * 8 + g;
-        const long stride = 4L * T * 8;
-        const int n = (nstrips - q + 3) / 4;
+        const double* base = part + ((long)q * T + t) * KP + g;
+        const long stride = (long)PHASES * T * KP;
+        const int n = (nstrips - q + PHASES - 1) / PHASES;
         int i = 0;
         for (; i + 8 <= n; i += 8) {
             double v[8];
@@ -80,18 +82,17 @@ kmeans_assign_kernel(const double* __restrict__ part, int nstrips, const double*
         for (; i < n; ++i) a0 += __ldcg(base + (long)i * stride);
     }
     const double v = a0 + a1;
-    // x.c_j: the four strip phases in fixed order
+    // x.c_j: the strip phases in fixed order
     double dot = __shfl_sync(CDR_FULL_MASK, v, g);
-    dot += __shfl_sync(CDR_FULL_MASK, v, g + 8);
-    dot += __shfl_sync(CDR_FULL_MASK, v, g + 16);
-    dot += __shfl_sync(CDR_FULL_MASK, v, g + 24);
+#pragma unroll
+    for (int ph = 1; ph < PHASES; ++ph) dot += __shfl_sync(CDR_FULL_MASK, v, g + ph * KP);
     double score = (g < k) ? cnorm[g] - 2.0 * dot : INFINITY;
     int idx = g;
-    // first minimum over the 8 components: the smaller score wins, the lower index on a tie
+    // first minimum over the components: the smaller score wins, the lower index on a tie
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-        const double os = __shfl_xor_sync(CDR_FULL_MASK, score, o, 8);
-        const int oi = __shfl_xor_sync(CDR_FULL_MASK, idx, o, 8);
+    for (int o = KP / 2; o > 0; o >>= 1) {
+        const double os = __shfl_xor_sync(CDR_FULL_MASK, score, o, KP);
+        const int oi = __shfl_xor_sync(CDR_FULL_MASK, idx, o, KP);
         if (os < score || (os == score && oi < idx)) {
             score = os;
             idx = oi;
@@ -214,7 +215,7 @@ static double* kmeans_slice_part(const cdr_kmeans_problem* p)
 
 extern "C" int cdr_kmeans_fused_applicable(int T, int d, int k)
 {
-    if (k > 8) return 0;
+    if (k > 16) return 0;
     int out[12];
     tma_stream_plan(T, d, k, 0, out);
     int TC, nstrips;
@@ -261,8 +262,14 @@ extern "C" int cdr_kmeans_iterate_enqueue(const cdr_kmeans_problem* p, cdr_strea
                                                p->workspace, p->workspace_bytes, flags, s, nullptr);
         if (rc != 0) return rc == CDR_TMA_NOT_APPLICABLE ? CDR_ERR_NOT_APPLICABLE : rc;
     }
-    kmeans_assign_kernel<<<(T + 7) / 8, 256, 0, s>>>((const double*)p->workspace, nstrips, p->cnorm, T, k,
-                                                     p->labels, p->onehot, p->ldt, p->counts, p->state);
+    if (k <= 8)
+        kmeans_assign_kernel<8><<<(T + 7) / 8, 256, 0, s>>>((const double*)p->workspace, nstrips, p->cnorm,
+                                                            T, k, p->labels, p->onehot, p->ldt,
+                                                            p->counts, p->state);
+    else
+        kmeans_assign_kernel<16><<<(T + 7) / 8, 256, 0, s>>>((const double*)p->workspace, nstrips, p->cnorm,
+                                                             T, k, p->labels, p->onehot, p->ldt,
+                                                             p->counts, p->state);
     CDR_RETURN_IF_LAUNCH_FAILED();
     {
         const int rc = cdr_reduce_samples(p->onehot, p->ldt, 1, p->X, p->ldx, T, d, k, nullptr, p->sums,

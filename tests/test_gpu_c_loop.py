@@ -139,3 +139,23 @@ def test_kmeans_device_loop_relocates_an_empty_cluster():
     assert np.array_equal(labels, sk.labels_) and n_iter == sk.n_iter_
     np.testing.assert_allclose(inertia, sk.inertia_, rtol=1e-10)
     np.testing.assert_allclose(cent, sk.cluster_centers_, rtol=0, atol=1e-9)
+
+
+def test_kmeans_device_loop_twelve_clusters():
+    """The device Lloyd loop for 8 < k <= 16 (16 lanes per sample in the assignment kernel):
+    labels, iteration count and centres against scikit-learn from the same initial centres."""
+    from sklearn.cluster import KMeans as SkKMeans
+    from convex_dim_red.kmeans import kmeans_lloyd
+    T, d, k = 600, 25600, 12
+    assert be.library().cdr_kmeans_fused_applicable(T, d, k) == 1
+    rs = np.random.RandomState(9)
+    centres = rs.standard_normal((k, d)) * 1.5
+    X = centres[rs.randint(k, size=T)] + rs.standard_normal((T, d))
+    init = X[rs.choice(T, size=k, replace=False)].copy()
+    stats = {}
+    labels, cent, inertia, n_iter = kmeans_lloyd(X, init, tol=1e-4, max_iter=300, stats=stats)
+    sk = SkKMeans(n_clusters=k, init=init, n_init=1, algorithm='lloyd', tol=1e-4, max_iter=300).fit(X)
+    assert stats['device_loop']
+    assert np.array_equal(labels, sk.labels_) and n_iter == sk.n_iter_
+    np.testing.assert_allclose(inertia, sk.inertia_, rtol=1e-10)
+    np.testing.assert_allclose(cent, sk.cluster_centers_, rtol=0, atol=1e-9)

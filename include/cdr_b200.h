@@ -312,7 +312,7 @@ int cdr_center_columns(double* X, long ldx, int T, int d, const double* mean, do
  * data; `counts` is int[k]; the state block starts zeroed except max_iter and tol_abs.  An
  * empty cluster stops the loop before the centre update with needs_relocation set (the caller
  * relocates and finishes that iteration with the stand-alone calls above).  Returns
- * CDR_ERR_NOT_APPLICABLE for shapes the strip kernels do not cover or k > 8. */
+ * CDR_ERR_NOT_APPLICABLE for shapes the strip kernels do not cover or k > 16. */
 typedef struct cdr_kmeans_state {
     int done;              /* must stay first (the streaming kernels read it as cdr_flags) */
     int n_iter;            /* completed Lloyd iterations */

@@ -82,6 +82,8 @@ def parse_args():
                     help='N > 1: skip the strong-scaling (fixed total size) measurements')
     ap.add_argument('--no-kmeans', action='store_true',
                     help='skip the k-means block (BASELINE configs[2])')
+    ap.add_argument('--no-gram', action='store_true',
+                    help="skip the nested AA block measured through formulation='gram'")
     ap.add_argument('--no-numba', action='store_true',
                     help='reference arm: skip timing the real (Numba) reference from baseline/_ref')
     return ap.parse_args()
@@ -473,6 +475,40 @@ def workload_block(args, workload, X, Xd, rank, world, comm, sampler, hbm_peak, 
     return block
 
 
+def gram_block(args, X, Xd):
+    """AA through the opt-in Gram formulation: K = X X' is built once by
+    the SYRK kernel and the alternating loop runs on the L2-resident K -- the same iteration
+    in exact arithmetic, so it is reported next to the streaming numbers, never as them."""
+    import copy
+    import bench_harness as bh
+    from convex_dim_red import _backend as be
+    T, d, k = args.rows, args.features, args.components
+    Z0, C0 = initial_factors('aa', T, d, k, 0, 1)
+    gargs = copy.copy(args)
+    gargs.formulation = 'gram'
+    res = bh.run_workload(gargs, 'aa', X, Z0, C0, Xd, 0, 1, None)
+    res.pop('engine')
+    res.pop('step')
+    t_gram = bh.time_launches(lambda: be.gram(Xd, T, d), reps=3)
+    ttc = bh.run_to_convergence('aa', X, Z0, C0, formulation='gram')
+    ref = bh.gpu_fit('aa', X, Z0, C0, 5)
+    from convex_dim_red import archetypal_analysis as aa
+    out = aa._iterate_aa(X, Z0, C0, np.ones(k), tolerance=0.0, max_iterations=5,
+                         dictionary_solver_kwargs=bh.DICT_KW, require_monotonic_cost_decrease=False,
+                         formulation='gram')
+    return {'what': "archetypal analysis with formulation='gram': K = X X' (T x T) built once, "
+                    'iterations on K (general kernel sequence)',
+            'value': 1e3 / res['ms_per_step'], 'unit': 'iterations/s', 'ms_per_step': res['ms_per_step'],
+            'launches_per_step': res['launches_per_step'], 'gram_build_ms': t_gram,
+            'gram_build_tflops': 2.0 * T * T * d / (t_gram * 1e-3) / 1e12,
+            'gram_build_executed_tflops': 1.0 * T * T * d / (t_gram * 1e-3) / 1e12,   # upper triangle
+            'time_to_converge': ttc,
+            'agreement_with_streaming': {
+                'iterations': 5, 'streaming_cost': ref[2], 'gram_cost': float(out[3]),
+                'cost_rel_diff': abs(float(out[3]) - ref[2]) / abs(ref[2]),
+                'weights_max_abs_diff': float(np.max(np.abs(out[0] - ref[0])))}}
+
+
 def fixed_size_block(args, name, workload, X, Xd, Z0, F0, rank, world, comm, flops_per_step):
     """A fixed-total-size (strong scaling) measurement: this rank's rows of the problem."""
     import bench_harness as bh
@@ -619,6 +655,9 @@ def run_b200(args):
     for wl in workloads:
         blocks[wl] = workload_block(args, wl, X, Xd, rank, world, comm, sampler, hbm_peak, peak_src)
     sampler.__exit__(None, None, None)
+    gram = None
+    if world == 1 and 'aa' in workloads and args.formulation == 'stream' and not args.no_gram:
+        gram = gram_block(args, X, Xd)
     del Xd
     torch.cuda.empty_cache()
     strong = strong_scaling(args, rank, world, comm)
@@ -630,6 +669,8 @@ def run_b200(args):
         if len(workloads) > 1:
             head['gpnh'] = blocks['gpnh']
             head['gpu_launches'] += blocks['gpnh']['gpu_launches']
+        if gram:
+            blocks['aa']['gram_formulation'] = gram
         if strong:
             head['strong_scaling'] = strong
         if kmeans:

@@ -132,6 +132,43 @@ def test_qp_batched_pinned_iterations(k):
         assert np.all(Z >= 0)
 
 
+@pytest.mark.parametrize('k', [1, 2, 5, 8, 13, 64])
+def test_qp_projection_of_the_start_on_hard_inputs(k):
+    """With max_iterations = 0 the batched solver returns P(z0) (spg.py:300), i.e. the
+    per-sample threshold search on its own (k <= 8: rank / ballot form, k > 8: Michelot):
+    ties, vertices, all-equal, already feasible, feasible up to rounding, huge and tiny
+    magnitudes, against simplex_projection.py:13-27 as restated by the oracle."""
+    rs = np.random.RandomState(40 + k)
+    rows = [np.full(k, 1.0 / k), np.zeros(k), np.full(k, 7.5), -np.arange(k, dtype=float)]
+    e = np.zeros(k)
+    e[k // 2] = 1.0
+    rows.append(e.copy())
+    e[k // 2] = 100.0
+    rows.append(e.copy())
+    v = rs.rand(k)
+    v[: max(1, k // 2)] = v[0]
+    rows.append(v.copy())                                  # ties among the largest
+    v = rs.rand(k)
+    v /= v.sum()
+    rows += [v.copy(), v + 1e-17, v * (1 + 1e-15), v - 1e-16]
+    rows += [rs.standard_normal(k) * 1e6, rs.standard_normal(k) * 1e-9, 1.0 + rs.standard_normal(k) * 1e-13]
+    for scale in (0.1, 1.0, 10.0):
+        rows += list(rs.standard_normal((100, k)) * scale)
+    Z0 = np.array(rows)
+    T = Z0.shape[0]
+    Z, n_it, _ = _run_qp(np.eye(k), None, np.zeros((k, T)), Z0, True, max_iterations=0)
+    ref = orc.simplex_project_rows(Z0)
+    scale = np.maximum(1.0, np.abs(Z0).max(axis=1))[:, None]
+    err = np.abs(Z - ref).max(axis=1)
+    tol = 4e-16 * k * scale[:, 0]
+    assert np.all(err <= tol), (np.argmax(err / tol), Z0[np.argmax(err / tol)], err.max())
+    assert np.all(Z >= 0)
+    # the outputs sum to one as accurately as the oracle's do
+    sum_err, ref_sum_err = np.abs(Z.sum(axis=1) - 1.0), np.abs(ref.sum(axis=1) - 1.0)
+    worst = np.argmax(sum_err - ref_sum_err - tol)
+    assert np.all(sum_err <= ref_sum_err + tol), (worst, Z0[worst], sum_err[worst], ref_sum_err[worst])
+
+
 @pytest.mark.parametrize('k', [3, 8, 20, 64])
 def test_qp_batched_converged(k):
     T = 150

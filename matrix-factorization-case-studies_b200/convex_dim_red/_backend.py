@@ -532,6 +532,22 @@ def graphs_disabled():
     return os.environ.get('CDR_NO_CUDA_GRAPH', '0') == '1'
 
 
+def graph_after(c_loop):
+    """Outer iterations launched eagerly before the iteration is captured into a CUDA graph.
+
+    Capturing and instantiating costs 2.5-3 ms.  An engine on the whole-iteration C entry
+    points launches 3-9 kernels of ~0.1 ms each per outer iteration, so the host keeps far
+    ahead of the device without a graph and a short fit (a 20-iteration call is ~9 ms of device
+    time) should not pay for one; in a long fit the replayed graph's smaller launch gaps win
+    the cost back after ~150 iterations.  The general kernel sequences (12-25 short launches
+    per iteration) are captured right after the first iteration.  ``CDR_GRAPH_AFTER=n``
+    overrides."""
+    env = os.environ.get('CDR_GRAPH_AFTER')
+    if env is not None:
+        return max(1, int(env))
+    return 32 if c_loop else 1
+
+
 def graph_collectives():
     """Whether NCCL collectives are captured into the iteration graph (``CDR_GRAPH_NCCL``,
     default on; set to 0 to launch sharded iterations eagerly)."""

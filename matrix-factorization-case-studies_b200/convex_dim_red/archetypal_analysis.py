@@ -375,8 +375,9 @@ class _AaEngine:
             print('{:12d} | {: 12.6e} | {: 12.6e}'.format(st.n_iter, st.cost, st.cost - st.old_cost))
         chunk = 1
         graph = None
+        graph_after = be.graph_after(self.c_loop)
         while not st.done and launched < max_it:
-            if use_graph and graph is None:
+            if use_graph and graph is None and launched >= graph_after:
                 graph = be.capture_graph(self.iteration)
                 be.trace('aa: graph capture')
             n = min(chunk, max_it - launched)
@@ -390,7 +391,9 @@ class _AaEngine:
             if verbose:
                 print('{:12d} | {: 12.6e} | {: 12.6e}'.format(
                     st.n_iter, st.cost, st.cost - st.old_cost))
-            elif chunk < 32 and graph is not None:
+            elif chunk < 32 and (graph is not None or self.c_loop):
+                # (past `done` the kernels of an iteration return at once, so a chunk may
+                # overshoot; the host-paced general sequence is not launched ahead)
                 chunk *= 2
         torch.cuda.synchronize()
         elapsed = time.perf_counter() - start

@@ -251,8 +251,9 @@ class _GpnhEngine:
         st = self.state.read()
         chunk = 1
         graph = None
+        graph_after = be.graph_after(self.c_loop)
         while not st.done and launched < max_it:
-            if use_graph and graph is None and not verbose:
+            if use_graph and graph is None and not verbose and launched >= graph_after:
                 be.trace('gpnh: first iteration')
                 graph = be.capture_graph(self.iteration)
                 be.trace('gpnh: graph capture')

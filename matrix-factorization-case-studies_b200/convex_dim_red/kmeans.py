@@ -255,7 +255,8 @@ def kmeans_lloyd(X, init_centres, tol=1e-4, max_iter=300, verbose=False, comm=No
             t1.record()
             torch.cuda.synchronize()
             return t0.elapsed_time(t1) / int(_time_iterations)
-        graph, chunk = None, 1
+        graph, chunk, launched = None, 1, 1
+        graph_after = be.graph_after(True)               # a Lloyd iteration is 4 long kernels
         while True:
             if st.done and st.needs_relocation:
                 # the device stopped before the centre update: finish this iteration here
@@ -274,7 +275,7 @@ def kmeans_lloyd(X, init_centres, tol=1e-4, max_iter=300, verbose=False, comm=No
                 break
             if verbose:
                 print('Iteration %d, center shift %.6e' % (st.n_iter - 1, st.shift_total))
-            elif graph is None and not be.graphs_disabled():
+            elif graph is None and launched >= graph_after and not be.graphs_disabled():
                 graph = be.capture_graph(iterate)
                 be.trace('kmeans: graph capture')
             for _ in range(1 if verbose else chunk):
@@ -282,6 +283,7 @@ def kmeans_lloyd(X, init_centres, tol=1e-4, max_iter=300, verbose=False, comm=No
                     graph.replay()
                 else:
                     iterate()
+            launched += 1 if verbose else chunk
             st = read_state()
             chunk = min(2 * chunk, 16)
         n_iter, strict = int(st.n_iter), bool(st.strict)

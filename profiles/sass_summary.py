@@ -28,7 +28,7 @@ def main():
     for name, body in zip(names, blocks):
         counts = collections.Counter()
         for line in body.splitlines():
-            m = re.search(r'/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)', line)
+            m = re.search(r'/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)', line)
             if m:
                 op = m.group(1).split('.')[0]
                 for k in KEYS:

@@ -216,7 +216,7 @@ gpnh_weights_fused_kernel(GpnhFusedArgs a)
         __syncthreads();
         const double pref = (k > 1) ? 4.0 / ((double)a.d * k * (k - 1)) : 0.0;
         CDR_TAIL_MARK(3);
-        solve_matrix_cta(S, k, kFusedMaxK, 1.0 / (double)a.T_total, a.lambda_W, pref, a.P, jac);
+        solve_matrix_cta<KP>(S, k, kFusedMaxK, 1.0 / (double)a.T_total, a.lambda_W, pref, a.P, jac);
     }
     CDR_TAIL_MARK(4);
     CDR_PHASE(5);

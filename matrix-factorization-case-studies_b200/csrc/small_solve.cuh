@@ -65,6 +65,10 @@ __device__ __forceinline__ int spd_inverse_warp(const double* A, int k, double s
 
 // All threads of the CTA call this together (blockDim.x a multiple of 32); jac_sm holds
 // 2 * kmax * kJacLd doubles of shared memory, kmax >= k.  ZtZ may be global or shared.
+// GJMAX: the widest Gauss-Jordan instantiation to compile in (8 / 16 in the fused iteration
+// kernels, whose k never exceeds that; the fully unrolled 32-wide variant is 2000 shuffles of
+// code).
+template <int GJMAX = CDR_MAX_GJ>
 __device__ __forceinline__ void solve_matrix_cta(const double* ZtZ, int k, int kmax, double inv_n,
                                                  double lambda_W, double gw_prefactor,
                                                  double* __restrict__ P, double* jac_sm)
@@ -93,12 +97,18 @@ __device__ __forceinline__ void solve_matrix_cta(const double* ZtZ, int k, int k
     // about a microsecond instead of ~50 for the Jacobi sweeps.  The pivots are those of the
     // Cholesky / LDL' factorisation; any of them below 1e-10 * max diag falls through to the
     // pseudo-inverse, which reproduces lstsq's minimum-norm solution for singular Z'Z.
-    if (k <= CDR_MAX_GJ) {
+    if (k <= GJMAX) {
         if (tid < 32) {
-            int ok;
-            if (k <= 8) ok = spd_inverse_warp<8>(A, k, inv_n, P);
-            else if (k <= 16) ok = spd_inverse_warp<16>(A, k, inv_n, P);
-            else ok = spd_inverse_warp<CDR_MAX_GJ>(A, k, inv_n, P);
+            int ok = 0;
+            if (k <= 8) {
+                ok = spd_inverse_warp<8>(A, k, inv_n, P);
+            } else if constexpr (GJMAX > 8) {
+                if (k <= 16) {
+                    ok = spd_inverse_warp<16>(A, k, inv_n, P);
+                } else if constexpr (GJMAX > 16) {
+                    ok = spd_inverse_warp<GJMAX>(A, k, inv_n, P);
+                }
+            }
             if (tid == 0) chol_ok = ok;
         }
         __syncthreads();

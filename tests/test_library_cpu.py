@@ -303,3 +303,26 @@ def test_preprocessing_host_helpers():
     assert train.shape == (9, 10) and val.shape == (1, 10) and np.array_equal(missing, missing2)
     with pytest.raises(ValueError):
         pp.weight_and_flatten(field[0], w)
+
+
+def test_graph_capture_policy(monkeypatch):
+    """Engines on the whole-iteration C entry points launch 32 iterations eagerly before they
+    capture the iteration graph (a capture costs more than a short call's launches); the
+    general kernel sequences capture right after the first iteration; CDR_GRAPH_AFTER
+    overrides both; CDR_LIBRARY selects another build of the library."""
+    from convex_dim_red import _backend as be
+    monkeypatch.delenv('CDR_GRAPH_AFTER', raising=False)
+    assert be.graph_after(True) == 32 and be.graph_after(False) == 1
+    monkeypatch.setenv('CDR_GRAPH_AFTER', '5')
+    assert be.graph_after(True) == 5 and be.graph_after(False) == 5
+    monkeypatch.setenv('CDR_GRAPH_AFTER', '0')
+    assert be.graph_after(True) == 1
+    assert be.LIB_PATH.endswith('libcdr_b200.so')
+
+
+def test_kmeans_device_loop_covers_sixteen_clusters(lib):
+    # shape-only query (no GPU needed): the strip plan of BASELINE configs[2]
+    assert lib.cdr_kmeans_fused_applicable(700, 41800, 8) == 1
+    assert lib.cdr_kmeans_fused_applicable(700, 41800, 16) == 1
+    assert lib.cdr_kmeans_fused_applicable(700, 41800, 17) == 0
+    assert lib.cdr_kmeans_fused_applicable(60, 200, 4) == 0
